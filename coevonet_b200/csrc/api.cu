@@ -1,0 +1,185 @@
+// C ABI: handle management, error text, K1 entry points (include/coevonet_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace cev {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return CEV_OK;
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return CEV_ERR_CUDA;
+}
+
+}  // namespace cev
+
+using namespace cev;
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+extern "C" {
+
+int cev_version(void) { return 100; }
+
+const char* cev_last_error(void) { return g_err; }
+
+int cev_create(int device, cev_handle** out) {
+    CEV_REQUIRE(out != nullptr, "cev_create: null out");
+    int count = 0;
+    CEV_CUDA(cudaGetDeviceCount(&count));
+    CEV_REQUIRE(device >= 0 && device < count, "cev_create: device %d out of range (%d devices)", device, count);
+    CEV_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CEV_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("cev_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                  prop.minor);
+        return CEV_ERR_UNSUPPORTED;
+    }
+    cev_handle* h = new cev_handle();
+    h->device = device;
+    h->n_sm = prop.multiProcessorCount;
+    h->workspace = nullptr;
+    h->workspace_bytes = 0;
+    int ncl = rollout_cluster_max_clusters(device);
+    if (ncl <= 0) ncl = h->n_sm / 4 - 4;
+    h->n_clusters = ncl;
+    *out = h;
+    return CEV_OK;
+}
+
+int cev_destroy(cev_handle* h) {
+    if (!h) return CEV_OK;
+    if (h->workspace) cudaFree(h->workspace);
+    delete h;
+    return CEV_OK;
+}
+
+int cev_device_info(cev_handle* h, int* n_sm, int* n_clusters) {
+    CEV_REQUIRE(h != nullptr, "cev_device_info: null handle");
+    if (n_sm) *n_sm = h->n_sm;
+    if (n_clusters) *n_clusters = h->n_clusters;
+    return CEV_OK;
+}
+
+int cev_fc_dim(int in_dim) { return fc_offsets(in_dim).total; }
+int cev_fc_pitch(int in_dim) { return fc_pitch(in_dim); }
+
+int cev_dqn_dim(int c_in, int n_actions) {
+    return 32 * c_in * 64 + 32 + 64 * 32 * 16 + 64 + 64 * 64 * 9 + 64 + 512 * 3136 + 512 + n_actions * 512 +
+           n_actions + 2 * (32 + 64 + 64);
+}
+int cev_dqn_pitch(int c_in, int n_actions) { return round_up(cev_dqn_dim(c_in, n_actions), 32); }
+
+static int check_cfg(const cev_rollout_cfg* cfg) {
+    CEV_REQUIRE(cfg != nullptr, "rollout: null cfg");
+    CEV_REQUIRE(cfg->n_cycles >= 0 && cfg->n_cycles <= MAX_CYCLES, "rollout: n_cycles must be in [0, %d]", MAX_CYCLES);
+    CEV_REQUIRE(cfg->variant >= 0 && cfg->variant <= 2, "rollout: variant must be 0, 1 or 2");
+    return CEV_OK;
+}
+
+int cev_mpe_rollout_f32(cev_handle* h, int member_seat, const float* members, int P, int64_t member_pitch,
+                        const float* opp_a, int64_t opp_a_pitch, const float* opp_b, int64_t opp_b_pitch, int K,
+                        const double* init, int init_shared, int E, const cev_rollout_cfg* cfg, double* out,
+                        int32_t* status, cev_stream stream) {
+    CEV_REQUIRE(h && members && opp_a && opp_b && init && out, "mpe_rollout: null pointer");
+    CEV_REQUIRE(member_seat >= 0 && member_seat <= 2, "mpe_rollout: member_seat must be 0..2");
+    CEV_REQUIRE(P >= 0 && K >= 1 && E >= 1, "mpe_rollout: need P >= 0, K >= 1, E >= 1");
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    const int other[2] = {member_seat == 0 ? 1 : 0, member_seat == 2 ? 1 : 2};
+    CEV_REQUIRE(member_pitch >= fc_offsets(seat_in_dim(member_seat)).total && member_pitch % 4 == 0,
+                "mpe_rollout: member pitch too small / not a multiple of 4");
+    CEV_REQUIRE(opp_a_pitch >= fc_offsets(seat_in_dim(other[0])).total && opp_a_pitch % 4 == 0 &&
+                    opp_b_pitch >= fc_offsets(seat_in_dim(other[1])).total && opp_b_pitch % 4 == 0,
+                "mpe_rollout: opponent pitch too small / not a multiple of 4");
+    CEV_REQUIRE(aligned16(members) && aligned16(opp_a) && aligned16(opp_b), "mpe_rollout: rows must be 16B aligned");
+    if (P == 0) return CEV_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool use_cluster = cfg->variant == 2 || (cfg->variant == 0 && h->n_clusters > 0);
+    if (use_cluster) {
+        ClusterParams p{};
+        p.members = members;
+        p.member_pitch = member_pitch;
+        p.P = P;
+        p.opp[0] = opp_a;
+        p.opp[1] = opp_b;
+        p.opp_pitch[0] = opp_a_pitch;
+        p.opp_pitch[1] = opp_b_pitch;
+        p.K = K;
+        p.member_seat = member_seat;
+        p.init = init;
+        p.init_shared = init_shared;
+        p.E = E;
+        p.out = out;
+        p.status = status;
+        p.n_cycles = cfg->n_cycles;
+        p.pos_first = cfg->integrate_pos_first;
+        return launch_rollout_cluster(h, p, st);
+    }
+    GenericParams g{};
+    g.w[member_seat] = members;
+    g.pitch[member_seat] = member_pitch;
+    g.w[other[0]] = opp_a;
+    g.pitch[other[0]] = opp_a_pitch;
+    g.w[other[1]] = opp_b;
+    g.pitch[other[1]] = opp_b_pitch;
+    g.idx = nullptr;
+    g.member_seat = member_seat;
+    g.K = K;
+    g.E = E;
+    g.init_shared = init_shared;
+    g.init = init;
+    g.out = out;
+    g.status = status;
+    g.n_cycles = cfg->n_cycles;
+    g.pos_first = cfg->integrate_pos_first;
+    g.N = (int64_t)P * K * E;
+    return launch_rollout_generic(h, g, st);
+}
+
+int cev_mpe_rollout_indexed_f32(cev_handle* h, const float* w_adv, int64_t adv_pitch, const float* w_a0,
+                                int64_t a0_pitch, const float* w_a1, int64_t a1_pitch, const int32_t* idx,
+                                const double* init, int N, const cev_rollout_cfg* cfg, double* out,
+                                int32_t* status, cev_stream stream) {
+    CEV_REQUIRE(h && w_adv && w_a0 && w_a1 && idx && init && out, "mpe_rollout_indexed: null pointer");
+    CEV_REQUIRE(N >= 0, "mpe_rollout_indexed: N < 0");
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    CEV_REQUIRE(adv_pitch >= fc_offsets(IN_ADV).total && a0_pitch >= fc_offsets(IN_GOOD).total &&
+                    a1_pitch >= fc_offsets(IN_GOOD).total && adv_pitch % 4 == 0 && a0_pitch % 4 == 0 &&
+                    a1_pitch % 4 == 0,
+                "mpe_rollout_indexed: pitch too small / not a multiple of 4");
+    CEV_REQUIRE(aligned16(w_adv) && aligned16(w_a0) && aligned16(w_a1), "mpe_rollout_indexed: rows must be 16B aligned");
+    GenericParams g{};
+    g.w[0] = w_adv;
+    g.w[1] = w_a0;
+    g.w[2] = w_a1;
+    g.pitch[0] = adv_pitch;
+    g.pitch[1] = a0_pitch;
+    g.pitch[2] = a1_pitch;
+    g.idx = idx;
+    g.member_seat = 0;
+    g.K = 1;
+    g.E = 1;
+    g.init_shared = 0;
+    g.init = init;
+    g.out = out;
+    g.status = status;
+    g.n_cycles = cfg->n_cycles;
+    g.pos_first = cfg->integrate_pos_first;
+    g.N = N;
+    return launch_rollout_generic(h, g, (cudaStream_t)stream);
+}
+
+}  // extern "C"

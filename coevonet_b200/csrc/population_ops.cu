@@ -1,0 +1,471 @@
+// K3-K7: population-level GA / ES kernels over flat parameter rows.
+// All are streaming kernels (HBM-bound or Philox-ALU-bound): 128-bit accesses,
+// one float4 of parameters per thread, grids sized from the data.
+#include "common.cuh"
+
+namespace cev {
+
+constexpr int PT = 256;
+
+// ---------------------------------------------------------------------------
+// K3  GA re-population   (genetic_algorithm.py:32-48,255-290; agent.py:25-29)
+// child c>=1 = elites[(c-1)%E] + sigma*z ; child 0 = elites[0] unmutated.
+// Every parameter is mutated (LayerNorm gamma/beta too, Appendix C #8).
+// mul and add are rounded separately, like `param.data += noise`.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(PT) ga_repopulate_kernel(
+    const float* __restrict__ elites, int E, int D, int64_t pitch, float sigma,
+    uint32_t k0, uint32_t k1, uint32_t tag, uint32_t gen, int64_t row0,
+    float* __restrict__ out, float* __restrict__ noise_out) {
+    const int64_t r = blockIdx.x;
+    const int64_t c = row0 + r;                       // global member id
+    const int j4 = blockIdx.y * PT + threadIdx.x;
+    if ((int64_t)j4 * 4 >= pitch) return;
+    const int64_t parent = (c == 0) ? 0 : (c - 1) % E;
+    const float4 pv = *reinterpret_cast<const float4*>(elites + parent * pitch + (int64_t)j4 * 4);
+    float p[4] = {pv.x, pv.y, pv.z, pv.w};
+    float z[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c != 0) {
+        normal4(k0, k1, tag, gen, (uint32_t)c, (uint32_t)j4, z);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int j = j4 * 4 + i;
+            if (j < D) p[i] = __fadd_rn(p[i], __fmul_rn(sigma, z[i]));
+            else { p[i] = 0.f; z[i] = 0.f; }
+        }
+    }
+    *reinterpret_cast<float4*>(out + r * pitch + (int64_t)j4 * 4) = make_float4(p[0], p[1], p[2], p[3]);
+    if (noise_out)
+        *reinterpret_cast<float4*>(noise_out + r * pitch + (int64_t)j4 * 4) = make_float4(z[0], z[1], z[2], z[3]);
+}
+
+// ---------------------------------------------------------------------------
+// K5  ES perturbation   (agent.py:31-70): Linear parameters only.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(PT) es_perturb_kernel(
+    const float* __restrict__ theta, int in_dim, int64_t pitch, float sigma,
+    uint32_t k0, uint32_t k1, uint32_t tag, uint32_t gen, int64_t row0,
+    float* __restrict__ out, float* __restrict__ noise_out) {
+    const FcOffsets o = fc_offsets(in_dim);
+    const int64_t r = blockIdx.x;
+    const int64_t c = row0 + r;
+    const int j4 = blockIdx.y * PT + threadIdx.x;
+    if ((int64_t)j4 * 4 >= pitch) return;
+    const float4 pv = *reinterpret_cast<const float4*>(theta + (int64_t)j4 * 4);
+    float p[4] = {pv.x, pv.y, pv.z, pv.w};
+    float z[4];
+    normal4(k0, k1, tag, gen, (uint32_t)c, (uint32_t)j4, z);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int j = j4 * 4 + i;
+        if (j < o.total && fc_is_perturbable(o, j)) p[i] = __fadd_rn(p[i], __fmul_rn(sigma, z[i]));
+        else z[i] = 0.f;
+        if (j >= o.total) p[i] = 0.f;
+    }
+    *reinterpret_cast<float4*>(out + r * pitch + (int64_t)j4 * 4) = make_float4(p[0], p[1], p[2], p[3]);
+    if (noise_out)
+        *reinterpret_cast<float4*>(noise_out + r * pitch + (int64_t)j4 * 4) = make_float4(z[0], z[1], z[2], z[3]);
+}
+
+// ---------------------------------------------------------------------------
+// K6  ES update   (evolutionary_strategy.py:120-148)
+// delta = lr/(n*sigma) * sum_i (sigma*z_i) * F_i, noise regenerated from the
+// Philox key.  Members are split over blockIdx.y; partial sums are reduced in a
+// fixed order by the second kernel (deterministic, no atomics).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(PT) es_update_partial_kernel(
+    const double* __restrict__ fitness, int in_dim, int64_t pitch, float sigma,
+    uint32_t k0, uint32_t k1, uint32_t tag, uint32_t gen, int64_t row0, int64_t n_rows,
+    int n_split, float* __restrict__ partial) {
+    const FcOffsets o = fc_offsets(in_dim);
+    const int j4 = blockIdx.x * PT + threadIdx.x;
+    if ((int64_t)j4 * 4 >= pitch) return;
+    const int sp = blockIdx.y;
+    const int64_t per = (n_rows + n_split - 1) / n_split;
+    const int64_t r_lo = sp * per, r_hi = min(n_rows, r_lo + per);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    bool pert[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int j = j4 * 4 + i;
+        pert[i] = j < o.total && fc_is_perturbable(o, j);
+    }
+    if (pert[0] || pert[1] || pert[2] || pert[3]) {
+        for (int64_t r = r_lo; r < r_hi; ++r) {
+            const float f = (float)fitness[r];
+            float z[4];
+            normal4(k0, k1, tag, gen, (uint32_t)(row0 + r), (uint32_t)j4, z);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = fmaf(__fmul_rn(sigma, z[i]), f, acc[i]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (!pert[i]) acc[i] = 0.f;
+    *reinterpret_cast<float4*>(partial + (int64_t)sp * pitch + (int64_t)j4 * 4) =
+        make_float4(acc[0], acc[1], acc[2], acc[3]);
+}
+
+__global__ void __launch_bounds__(PT) es_update_finish_kernel(
+    const float* __restrict__ partial, int n_split, int64_t pitch, float coef,
+    float* __restrict__ delta) {
+    const int64_t j = (int64_t)blockIdx.x * PT + threadIdx.x;
+    if (j >= pitch) return;
+    float s = 0.f;
+    for (int sp = 0; sp < n_split; ++sp) s += partial[(int64_t)sp * pitch + j];
+    delta[j] = __fmul_rn(coef, s);
+}
+
+__global__ void __launch_bounds__(PT) axpy_kernel(float a, const float* __restrict__ x,
+                                                  float* __restrict__ y, int64_t n) {
+    const int64_t j = (int64_t)blockIdx.x * PT + threadIdx.x;
+    if (j < n) y[j] = __fadd_rn(y[j], __fmul_rn(a, x[j]));
+}
+
+// ---------------------------------------------------------------------------
+// K7  fitness-sharing distances   (utils/game_logic_functions.py:12-21)
+// d[i] = || pop[i] - ref ||_2 over the Linear parameters; one CTA per row.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(PT) diversity_dist_kernel(
+    const float* __restrict__ pop, int64_t pitch, const float* __restrict__ ref, int in_dim,
+    float* __restrict__ dist) {
+    const FcOffsets o = fc_offsets(in_dim);
+    const int64_t r = blockIdx.x;
+    const float* row = pop + r * pitch;
+    float acc = 0.f;
+    for (int j4 = threadIdx.x; (int64_t)j4 * 4 < pitch; j4 += PT) {
+        const float4 a = *reinterpret_cast<const float4*>(row + (int64_t)j4 * 4);
+        const float4 b = *reinterpret_cast<const float4*>(ref + (int64_t)j4 * 4);
+        const float d[4] = {a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int j = j4 * 4 + i;
+            if (j < o.total && fc_is_perturbable(o, j)) acc = fmaf(d[i], d[i], acc);
+        }
+    }
+    __shared__ float red[PT / 32];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < PT / 32; ++w) s += red[w];
+        dist[r] = sqrtf(s);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K4  selection   (genetic_algorithm.py:223-234)
+// k rounds of a block-wide arg-max with the order (value desc, index asc);
+// NaN ranks lowest.  Single CTA: P <= a few 1e5 and k <= 64 is latency-bound.
+// ---------------------------------------------------------------------------
+constexpr int SEL_T = 1024;
+constexpr int SEL_MAXK = 64;
+
+__device__ __forceinline__ bool sel_better(double va, int64_t ia, double vb, int64_t ib) {
+    // is (va, ia) ranked before (vb, ib)?
+    if (ib < 0) return ia >= 0;
+    if (ia < 0) return false;
+    if (va > vb) return true;
+    if (va < vb) return false;
+    return ia < ib;
+}
+
+__global__ void __launch_bounds__(SEL_T) select_topk_kernel(const double* __restrict__ fitness, int64_t P,
+                                                            int k, int64_t* __restrict__ idx_out) {
+    __shared__ int64_t chosen[SEL_MAXK];
+    __shared__ double wv[SEL_T / 32];
+    __shared__ int64_t wi[SEL_T / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int round = 0; round < k; ++round) {
+        double bv = 0.0;
+        int64_t bi = -1;
+        for (int64_t i = threadIdx.x; i < P; i += SEL_T) {
+            bool taken = false;
+            for (int c = 0; c < round; ++c) taken = taken || (chosen[c] == i);
+            if (taken) continue;
+            double v = fitness[i];
+            if (v != v) v = -CUDART_INF;          // NaN ranks lowest
+            if (sel_better(v, i, bv, bi)) { bv = v; bi = i; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+            const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (sel_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { wv[warp] = bv; wi[warp] = bi; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double v = wv[0];
+            int64_t ix = wi[0];
+            for (int w = 1; w < SEL_T / 32; ++w)
+                if (sel_better(wv[w], wi[w], v, ix)) { v = wv[w]; ix = wi[w]; }
+            chosen[round] = ix;
+            idx_out[round] = ix;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(PT) gather_rows_kernel(const float* __restrict__ src, int64_t pitch,
+                                                         const int64_t* __restrict__ idx,
+                                                         float* __restrict__ dst) {
+    const int64_t r = blockIdx.x;
+    const int64_t s = idx[r];
+    const int j4 = blockIdx.y * PT + threadIdx.x;
+    if ((int64_t)j4 * 4 >= pitch) return;
+    *reinterpret_cast<float4*>(dst + r * pitch + (int64_t)j4 * 4) =
+        *reinterpret_cast<const float4*>(src + s * pitch + (int64_t)j4 * 4);
+}
+
+// ---------------------------------------------------------------------------
+// synthetic inputs
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double u_pm1(uint32_t x) {
+    // uniform in (-1, 1): ((x + 0.5) * 2^-32) * 2 - 1, exact in fp64
+    return ((double)x + 0.5) * (2.0 / 4294967296.0) - 1.0;
+}
+
+__global__ void __launch_bounds__(PT) init_states_kernel(uint32_t k0, uint32_t k1, uint32_t stream_id,
+                                                         int64_t n, double* __restrict__ out) {
+    const int64_t r = (int64_t)blockIdx.x * PT + threadIdx.x;
+    if (r >= n) return;
+    const uint32_t tag = noise_tag(CEV_KIND_ENV, 0);
+    uint32_t w[12];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+        const U4 v = philox4x32_10(U4{(uint32_t)b, (uint32_t)r, stream_id, tag}, k0, k1);
+        w[4 * b] = v.x; w[4 * b + 1] = v.y; w[4 * b + 2] = v.z; w[4 * b + 3] = v.w;
+    }
+    double* o = out + r * CEV_INIT_STATE_DIM;
+    o[0] = (double)(w[0] & 1u);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) o[1 + i] = u_pm1(w[1 + i]);
+}
+
+__global__ void __launch_bounds__(PT) random_frames_kernel(uint32_t k0, uint32_t k1, int64_t n16,
+                                                           uint4* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * PT + threadIdx.x;
+    if (i >= n16) return;
+    const U4 v = philox4x32_10(U4{(uint32_t)i, (uint32_t)(i >> 32), 0u, noise_tag(CEV_KIND_FRAMES, 0)}, k0, k1);
+    out[i] = make_uint4(v.x, v.y, v.z, v.w);
+}
+
+__global__ void __launch_bounds__(PT) philox_words_kernel(uint32_t k0, uint32_t k1, uint32_t tag, uint32_t gen,
+                                                          int64_t member0, int64_t n_members, int64_t n4,
+                                                          uint4* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * PT + threadIdx.x;
+    if (i >= n_members * n4) return;
+    const int64_t m = i / n4, j4 = i % n4;
+    const U4 v = philox4x32_10(U4{(uint32_t)j4, (uint32_t)(member0 + m), gen, tag}, k0, k1);
+    out[i] = make_uint4(v.x, v.y, v.z, v.w);
+}
+
+// ---------------------------------------------------------------------------
+// FP32 FMA-pipe peak (roofline denominator for K1)
+// ---------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters) {
+    float2 a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = make_float2(threadIdx.x * 1e-3f + i, blockIdx.x * 1e-3f - i);
+    const float2 b = make_float2(0.999f, 1.001f), c = make_float2(1e-3f, -1e-3f);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (MODE == 1) a[i] = __ffma2_rn(a[i], b, c);
+            else { a[i].x = fmaf(a[i].x, b.x, c.x); a[i].y = fmaf(a[i].y, b.y, c.y); }
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i].x + a[i].y;
+    if (s == 123.456f) out[0] = s;       // keep the chain alive
+}
+
+}  // namespace cev
+
+using namespace cev;
+
+static inline void split_seed(uint64_t seed, uint32_t& k0, uint32_t& k1) {
+    k0 = (uint32_t)(seed & 0xFFFFFFFFull);
+    k1 = (uint32_t)(seed >> 32);
+}
+
+static int ensure_workspace(cev_handle* h, size_t bytes) {
+    if (h->workspace_bytes >= bytes) return CEV_OK;
+    if (h->workspace) cudaFree(h->workspace);
+    h->workspace = nullptr;
+    h->workspace_bytes = 0;
+    CEV_CUDA(cudaMalloc(&h->workspace, bytes));
+    h->workspace_bytes = bytes;
+    return CEV_OK;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+extern "C" {
+
+int cev_ga_repopulate_f32(cev_handle* h, const float* elites, int E, int D, int64_t pitch, float sigma,
+                          uint64_t seed, int role, uint32_t gen, int64_t row0, int64_t n_rows,
+                          float* out, float* noise_out, cev_stream stream) {
+    CEV_REQUIRE(h && elites && out, "ga_repopulate: null pointer");
+    CEV_REQUIRE(E >= 1 && D >= 1 && pitch >= D && pitch % 4 == 0, "ga_repopulate: bad E/D/pitch");
+    CEV_REQUIRE(aligned16(elites) && aligned16(out) && aligned16(noise_out), "ga_repopulate: 16B alignment");
+    CEV_REQUIRE(row0 >= 0 && n_rows >= 0 && row0 + n_rows <= 0xFFFFFFFFll, "ga_repopulate: bad row range");
+    if (n_rows == 0) return CEV_OK;
+    uint32_t k0, k1;
+    split_seed(seed, k0, k1);
+    dim3 grid((unsigned)n_rows, (unsigned)((pitch / 4 + PT - 1) / PT));
+    ga_repopulate_kernel<<<grid, PT, 0, (cudaStream_t)stream>>>(elites, E, D, pitch, sigma, k0, k1,
+                                                               noise_tag(CEV_KIND_GA, role), gen, row0, out,
+                                                               noise_out);
+    return check_cuda(cudaGetLastError(), "ga_repopulate_kernel");
+}
+
+int cev_gather_rows_f32(cev_handle* h, const float* src, int64_t pitch, const int64_t* idx, int n, float* dst,
+                        cev_stream stream) {
+    CEV_REQUIRE(h && src && idx && dst, "gather_rows: null pointer");
+    CEV_REQUIRE(pitch % 4 == 0 && aligned16(src) && aligned16(dst), "gather_rows: alignment");
+    if (n <= 0) return CEV_OK;
+    dim3 grid((unsigned)n, (unsigned)((pitch / 4 + PT - 1) / PT));
+    gather_rows_kernel<<<grid, PT, 0, (cudaStream_t)stream>>>(src, pitch, idx, dst);
+    return check_cuda(cudaGetLastError(), "gather_rows_kernel");
+}
+
+int cev_select_topk_f64(cev_handle* h, const double* fitness, int64_t P, int k, int64_t* idx_out,
+                        cev_stream stream) {
+    CEV_REQUIRE(h && fitness && idx_out, "select_topk: null pointer");
+    CEV_REQUIRE(k >= 1 && k <= SEL_MAXK && k <= P, "select_topk: need 1 <= k <= min(P, %d)", SEL_MAXK);
+    select_topk_kernel<<<1, SEL_T, 0, (cudaStream_t)stream>>>(fitness, P, k, idx_out);
+    return check_cuda(cudaGetLastError(), "select_topk_kernel");
+}
+
+int cev_es_perturb_f32(cev_handle* h, const float* theta, int in_dim, float sigma, uint64_t seed, int role,
+                       uint32_t gen, int64_t row0, int64_t n_rows, int64_t pitch, float* out, float* noise_out,
+                       cev_stream stream) {
+    CEV_REQUIRE(h && theta && out, "es_perturb: null pointer");
+    CEV_REQUIRE(in_dim == IN_ADV || in_dim == IN_GOOD, "es_perturb: in_dim must be 8 or 10");
+    CEV_REQUIRE(pitch >= fc_offsets(in_dim).total && pitch % 4 == 0, "es_perturb: bad pitch");
+    CEV_REQUIRE(aligned16(theta) && aligned16(out) && aligned16(noise_out), "es_perturb: 16B alignment");
+    CEV_REQUIRE(row0 >= 0 && n_rows >= 0 && row0 + n_rows <= 0xFFFFFFFFll, "es_perturb: bad row range");
+    if (n_rows == 0) return CEV_OK;
+    uint32_t k0, k1;
+    split_seed(seed, k0, k1);
+    dim3 grid((unsigned)n_rows, (unsigned)((pitch / 4 + PT - 1) / PT));
+    es_perturb_kernel<<<grid, PT, 0, (cudaStream_t)stream>>>(theta, in_dim, pitch, sigma, k0, k1,
+                                                            noise_tag(CEV_KIND_ES, role), gen, row0, out,
+                                                            noise_out);
+    return check_cuda(cudaGetLastError(), "es_perturb_kernel");
+}
+
+int cev_es_update_f32(cev_handle* h, const double* fitness, int in_dim, float sigma, float lr, int64_t n_total,
+                      uint64_t seed, int role, uint32_t gen, int64_t row0, int64_t n_rows, float* delta,
+                      cev_stream stream) {
+    CEV_REQUIRE(h && fitness && delta, "es_update: null pointer");
+    CEV_REQUIRE(in_dim == IN_ADV || in_dim == IN_GOOD, "es_update: in_dim must be 8 or 10");
+    CEV_REQUIRE(n_total >= 1 && n_rows >= 0 && sigma > 0.f, "es_update: bad n/sigma");
+    CEV_REQUIRE(aligned16(delta), "es_update: 16B alignment");
+    const int64_t pitch = fc_pitch(in_dim);
+    int n_split = (int)((n_rows + 63) / 64);
+    if (n_split > 16) n_split = 16;
+    if (n_split < 1) n_split = 1;
+    int rc = ensure_workspace(h, (size_t)n_split * pitch * sizeof(float));
+    if (rc) return rc;
+    uint32_t k0, k1;
+    split_seed(seed, k0, k1);
+    float* partial = static_cast<float*>(h->workspace);
+    dim3 grid((unsigned)((pitch / 4 + PT - 1) / PT), (unsigned)n_split);
+    es_update_partial_kernel<<<grid, PT, 0, (cudaStream_t)stream>>>(fitness, in_dim, pitch, sigma, k0, k1,
+                                                                   noise_tag(CEV_KIND_ES, role), gen, row0,
+                                                                   n_rows, n_split, partial);
+    CEV_CUDA(cudaGetLastError());
+    // coefficient in fp64 like the reference's Python float, then one fp32 multiply
+    const float coef = (float)((double)lr / ((double)n_total * (double)sigma));
+    es_update_finish_kernel<<<(unsigned)((pitch + PT - 1) / PT), PT, 0, (cudaStream_t)stream>>>(partial, n_split,
+                                                                                              pitch, coef, delta);
+    return check_cuda(cudaGetLastError(), "es_update kernels");
+}
+
+int cev_axpy_f32(cev_handle* h, float a, const float* x, float* y, int64_t n, cev_stream stream) {
+    CEV_REQUIRE(h && x && y && n >= 0, "axpy: bad arguments");
+    if (n == 0) return CEV_OK;
+    axpy_kernel<<<(unsigned)((n + PT - 1) / PT), PT, 0, (cudaStream_t)stream>>>(a, x, y, n);
+    return check_cuda(cudaGetLastError(), "axpy_kernel");
+}
+
+int cev_diversity_dist_f32(cev_handle* h, const float* pop, int64_t n_rows, int64_t pitch, const float* ref,
+                           int in_dim, float* dist, cev_stream stream) {
+    CEV_REQUIRE(h && pop && ref && dist, "diversity_dist: null pointer");
+    CEV_REQUIRE(in_dim == IN_ADV || in_dim == IN_GOOD, "diversity_dist: in_dim must be 8 or 10");
+    CEV_REQUIRE(pitch >= fc_offsets(in_dim).total && pitch % 4 == 0, "diversity_dist: bad pitch");
+    CEV_REQUIRE(aligned16(pop) && aligned16(ref), "diversity_dist: 16B alignment");
+    if (n_rows <= 0) return CEV_OK;
+    diversity_dist_kernel<<<(unsigned)n_rows, PT, 0, (cudaStream_t)stream>>>(pop, pitch, ref, in_dim, dist);
+    return check_cuda(cudaGetLastError(), "diversity_dist_kernel");
+}
+
+int cev_init_states_f64(cev_handle* h, uint64_t seed, uint32_t stream_id, int64_t n, double* out,
+                        cev_stream stream) {
+    CEV_REQUIRE(h && out && n >= 0 && n <= 0xFFFFFFFFll, "init_states: bad arguments");
+    if (n == 0) return CEV_OK;
+    uint32_t k0, k1;
+    split_seed(seed, k0, k1);
+    init_states_kernel<<<(unsigned)((n + PT - 1) / PT), PT, 0, (cudaStream_t)stream>>>(k0, k1, stream_id, n, out);
+    return check_cuda(cudaGetLastError(), "init_states_kernel");
+}
+
+int cev_random_frames_u8(cev_handle* h, uint64_t seed, int64_t n_bytes, uint8_t* out, cev_stream stream) {
+    CEV_REQUIRE(h && out && n_bytes >= 0 && n_bytes % 16 == 0 && aligned16(out), "random_frames: bad arguments");
+    if (n_bytes == 0) return CEV_OK;
+    uint32_t k0, k1;
+    split_seed(seed, k0, k1);
+    const int64_t n16 = n_bytes / 16;
+    random_frames_kernel<<<(unsigned)((n16 + PT - 1) / PT), PT, 0, (cudaStream_t)stream>>>(
+        k0, k1, n16, reinterpret_cast<uint4*>(out));
+    return check_cuda(cudaGetLastError(), "random_frames_kernel");
+}
+
+int cev_philox_words(cev_handle* h, uint64_t seed, int kind, int role, uint32_t gen, int64_t member0,
+                     int64_t n_members, int64_t n4, uint32_t* out, cev_stream stream) {
+    CEV_REQUIRE(h && out && n_members >= 0 && n4 >= 0 && aligned16(out), "philox_words: bad arguments");
+    if (n_members * n4 == 0) return CEV_OK;
+    uint32_t k0, k1;
+    split_seed(seed, k0, k1);
+    const int64_t n = n_members * n4;
+    philox_words_kernel<<<(unsigned)((n + PT - 1) / PT), PT, 0, (cudaStream_t)stream>>>(
+        k0, k1, noise_tag(kind, role), gen, member0, n_members, n4, reinterpret_cast<uint4*>(out));
+    return check_cuda(cudaGetLastError(), "philox_words_kernel");
+}
+
+int cev_fp32_peak(cev_handle* h, int mode, double* tflops, cev_stream stream) {
+    CEV_REQUIRE(h && tflops, "fp32_peak: null pointer");
+    int rc = ensure_workspace(h, 256);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int iters = 4096, blocks = h->n_sm * 8;
+    cudaEvent_t e0, e1;
+    CEV_CUDA(cudaEventCreate(&e0));
+    CEV_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        CEV_CUDA(cudaEventRecord(e0, st));
+        if (mode == 1) fp32_peak_kernel<1><<<blocks, 256, 0, st>>>((float*)h->workspace, iters);
+        else fp32_peak_kernel<0><<<blocks, 256, 0, st>>>((float*)h->workspace, iters);
+        CEV_CUDA(cudaEventRecord(e1, st));
+        CEV_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CEV_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double flops = (double)blocks * 256.0 * iters * 16.0 * 2.0;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    return CEV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,275 @@
+"""Torch-facing wrappers of the C-ABI kernels (device tensors in, device tensors out).
+
+PyTorch is plumbing here: it owns device memory and streams; every operation
+below is one call into ``libcoevonet_b200.so`` on the current CUDA stream.
+There is no CPU path: non-CUDA tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib, layout
+from ._lib import RolloutCfg, check, handle, load
+
+MAX_CYCLES = 25
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _need_cuda(*tensors):
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise _lib.CevError("coevonet_b200 ops need CUDA tensors (no CPU fallback)")
+        if not t.is_contiguous():
+            raise _lib.CevError("coevonet_b200 ops need contiguous tensors")
+        dev = t.device if dev is None else dev
+        if t.device != dev:
+            raise _lib.CevError("all tensors of one op must live on the same device")
+    return dev
+
+
+def cycles_for_limit(agent_step_limit):
+    """World steps executed under ``play_MPE``'s agent-step limit
+    (``utils/game_logic_functions.py:127,195-210``; truncation after 25 cycles)."""
+    if agent_step_limit is None:
+        return MAX_CYCLES
+    return int(min(MAX_CYCLES, max(0, int(agent_step_limit)) // 3))
+
+
+def reward_slots(out, agent_step_limit=None, reference_compat=True):
+    """Map the kernel's physical sums ``out[..., 4]`` to the triple ``play_game``
+    returns ``(agent_0, agent_1, adversary_0)``.
+
+    ``reference_compat`` reproduces the rotated attribution of
+    ``utils/game_logic_functions.py:179-190``: agent_0's
+    and adversary_0's slots hold the good agents' reward up to the previous
+    cycle, agent_1's slot the adversary's.  ``False`` credits each role its own
+    reward sum."""
+    sg, lg, sa = out[..., 0], out[..., 1], out[..., 2]
+    if not reference_compat:
+        return sg, sg, sa
+    L = 75 if agent_step_limit is None else int(min(75, max(0, int(agent_step_limit))))
+    nc = L // 3
+    if nc == 0:
+        z = torch.zeros_like(sg)
+        return z, sa, z
+    n_adv = -(-L // 3)
+    n_a0 = -(-(L - 1) // 3)
+    slot_adv = sg if n_adv - 1 >= nc else sg - lg
+    slot_a0 = sg if n_a0 - 1 >= nc else sg - lg
+    return slot_a0, sa, slot_adv
+
+
+def raise_on_status(status):
+    """Surface device-detected faults as the reference's ``ValueError``
+    (``MPE/fcnetwork.py:39-65``).  Synchronises."""
+    code = int(status.item())
+    if code & _lib.STATUS_NONFINITE:
+        raise ValueError("\n\t Warning: output contains inf or NaN")
+
+
+def mpe_rollout(member_role, members, opp_a, opp_b, init, *, n_cycles=MAX_CYCLES,
+                pos_first=True, init_shared=False, variant=0, out=None, status=None):
+    """K1 structured rollout.
+
+    members fp32[P, pitch]; opp_a / opp_b fp32[K, pitch] for the two other seats
+    in ascending seat order (adversary_0 < agent_0 < agent_1); init fp64
+    [P, K, E, 11] (or [K, E, 11] with ``init_shared``).  Returns fp64 [P, K, E, 4].
+    """
+    dev = _need_cuda(members, opp_a, opp_b, init, out, status)
+    seat = layout.SEAT_OF[member_role] if isinstance(member_role, str) else int(member_role)
+    P, K = members.shape[0], opp_a.shape[0]
+    if opp_b.shape[0] != K:
+        raise _lib.CevError("opp_a and opp_b must hold the same number of rows")
+    if init_shared:
+        if init.dim() != 3 or init.shape[0] != K or init.shape[2] != _lib.INIT_STATE_DIM:
+            raise _lib.CevError("shared init must be fp64 [K, E, 11]")
+        E = init.shape[1]
+    else:
+        if init.dim() != 4 or init.shape[:2] != (P, K) or init.shape[3] != _lib.INIT_STATE_DIM:
+            raise _lib.CevError("init must be fp64 [P, K, E, 11]")
+        E = init.shape[2]
+    if members.dtype != torch.float32 or init.dtype != torch.float64:
+        raise _lib.CevError("members must be float32 and init float64")
+    if out is None:
+        out = torch.empty((P, K, E, _lib.ROLLOUT_OUT_DIM), dtype=torch.float64, device=dev)
+    cfg = RolloutCfg(int(n_cycles), int(bool(pos_first)), int(variant), 0)
+    check(load().cev_mpe_rollout_f32(
+        handle(dev.index), seat, _ptr(members), P, members.stride(0),
+        _ptr(opp_a), opp_a.stride(0), _ptr(opp_b), opp_b.stride(0), K,
+        _ptr(init), int(bool(init_shared)), E, ctypes.byref(cfg), _ptr(out), _ptr(status),
+        _stream(dev)), "cev_mpe_rollout_f32")
+    return out
+
+
+def mpe_rollout_indexed(w_adv, w_a0, w_a1, idx, init, *, n_cycles=MAX_CYCLES, pos_first=True,
+                        out=None, status=None):
+    """K1 indexed rollout: episode e is played by rows ``idx[e] = (adv, a0, a1)``."""
+    dev = _need_cuda(w_adv, w_a0, w_a1, idx, init, out, status)
+    N = idx.shape[0]
+    if idx.dtype != torch.int32 or init.dtype != torch.float64 or init.shape != (N, _lib.INIT_STATE_DIM):
+        raise _lib.CevError("idx must be int32 [N,3] and init fp64 [N,11]")
+    if out is None:
+        out = torch.empty((N, _lib.ROLLOUT_OUT_DIM), dtype=torch.float64, device=dev)
+    cfg = RolloutCfg(int(n_cycles), int(bool(pos_first)), 1, 0)
+    check(load().cev_mpe_rollout_indexed_f32(
+        handle(dev.index), _ptr(w_adv), w_adv.stride(0), _ptr(w_a0), w_a0.stride(0),
+        _ptr(w_a1), w_a1.stride(0), _ptr(idx), _ptr(init), N, ctypes.byref(cfg), _ptr(out),
+        _ptr(status), _stream(dev)), "cev_mpe_rollout_indexed_f32")
+    return out
+
+
+def ga_repopulate(elites, dim, sigma, seed, role, gen, row0, n_rows, *, out=None, noise_out=None):
+    """K3: rows [row0, row0+n_rows) of the next GA population."""
+    dev = _need_cuda(elites, out, noise_out)
+    pitch = elites.stride(0)
+    if out is None:
+        out = torch.empty((n_rows, pitch), dtype=torch.float32, device=dev)
+    role_id = layout.ROLE_ID[role] if isinstance(role, str) else int(role)
+    check(load().cev_ga_repopulate_f32(
+        handle(dev.index), _ptr(elites), elites.shape[0], int(dim), pitch, float(sigma),
+        int(seed), role_id, int(gen), int(row0), int(n_rows), _ptr(out), _ptr(noise_out),
+        _stream(dev)), "cev_ga_repopulate_f32")
+    return out
+
+
+def gather_rows(src, idx, *, out=None):
+    dev = _need_cuda(src, idx, out)
+    if idx.dtype != torch.int64:
+        raise _lib.CevError("gather_rows: idx must be int64")
+    if out is None:
+        out = torch.empty((idx.shape[0], src.stride(0)), dtype=torch.float32, device=dev)
+    check(load().cev_gather_rows_f32(handle(dev.index), _ptr(src), src.stride(0), _ptr(idx),
+                                     idx.shape[0], _ptr(out), _stream(dev)), "cev_gather_rows_f32")
+    return out
+
+
+def select_topk(fitness, k):
+    """K4: int64[k] indices of the k largest fitness values (desc, ties -> lower index)."""
+    dev = _need_cuda(fitness)
+    if fitness.dtype != torch.float64 or fitness.dim() != 1:
+        raise _lib.CevError("select_topk: fitness must be float64 [P]")
+    idx = torch.empty(k, dtype=torch.int64, device=dev)
+    check(load().cev_select_topk_f64(handle(dev.index), _ptr(fitness), fitness.shape[0], int(k),
+                                     _ptr(idx), _stream(dev)), "cev_select_topk_f64")
+    return idx
+
+
+def es_perturb(theta, in_dim, sigma, seed, role, gen, row0, n_rows, *, out=None, noise_out=None):
+    """K5: perturbed member rows theta + sigma*N(0,1) (Linear parameters only)."""
+    dev = _need_cuda(theta, out, noise_out)
+    pitch = layout.fc_pitch(in_dim)
+    if theta.numel() < pitch:
+        raise _lib.CevError("es_perturb: theta must be a padded flat row")
+    if out is None:
+        out = torch.empty((n_rows, pitch), dtype=torch.float32, device=dev)
+    role_id = layout.ROLE_ID[role] if isinstance(role, str) else int(role)
+    check(load().cev_es_perturb_f32(
+        handle(dev.index), _ptr(theta), int(in_dim), float(sigma), int(seed), role_id, int(gen),
+        int(row0), int(n_rows), pitch, _ptr(out), _ptr(noise_out), _stream(dev)), "cev_es_perturb_f32")
+    return out
+
+
+def es_update(fitness, in_dim, sigma, lr, n_total, seed, role, gen, row0, *, out=None):
+    """K6: delta fp32[pitch] = lr/(n_total*sigma) * sum_i (sigma z_i) fitness_i over the
+    local members [row0, row0+len(fitness))."""
+    dev = _need_cuda(fitness, out)
+    if fitness.dtype != torch.float64:
+        raise _lib.CevError("es_update: fitness must be float64")
+    pitch = layout.fc_pitch(in_dim)
+    if out is None:
+        out = torch.empty(pitch, dtype=torch.float32, device=dev)
+    role_id = layout.ROLE_ID[role] if isinstance(role, str) else int(role)
+    check(load().cev_es_update_f32(
+        handle(dev.index), _ptr(fitness), int(in_dim), float(sigma), float(lr), int(n_total),
+        int(seed), role_id, int(gen), int(row0), fitness.shape[0], _ptr(out), _stream(dev)),
+        "cev_es_update_f32")
+    return out
+
+
+def axpy(a, x, y):
+    dev = _need_cuda(x, y)
+    check(load().cev_axpy_f32(handle(dev.index), float(a), _ptr(x), _ptr(y), min(x.numel(), y.numel()),
+                              _stream(dev)), "cev_axpy_f32")
+    return y
+
+
+def diversity_dist(pop, ref, in_dim, *, out=None):
+    """K7: fp32[P] distances || pop[i] - ref || over the Linear parameters."""
+    dev = _need_cuda(pop, ref, out)
+    if out is None:
+        out = torch.empty(pop.shape[0], dtype=torch.float32, device=dev)
+    check(load().cev_diversity_dist_f32(handle(dev.index), _ptr(pop), pop.shape[0], pop.stride(0),
+                                        _ptr(ref), int(in_dim), _ptr(out), _stream(dev)),
+          "cev_diversity_dist_f32")
+    return out
+
+
+def diversity_from_dist(dist):
+    """The scalar of ``diversity_penalty`` (``utils/game_logic_functions.py:22-37``)
+    from the distances: sigma = mean(d), sum(max(0, 1 - d/sigma)).  P scalars of
+    glue arithmetic, done with torch on the device."""
+    sigma = dist.mean()
+    return torch.clamp(1 - dist / sigma, min=0).sum()
+
+
+def deepqn_forward(members, frames, c_in, n_actions):
+    """K2: logits fp32[P,B,A] and first-max actions int32[P,B]."""
+    dev = _need_cuda(members, frames)
+    P, B = frames.shape[0], frames.shape[1]
+    if frames.dtype != torch.uint8 or tuple(frames.shape[2:]) != (c_in, 84, 84):
+        raise _lib.CevError("deepqn_forward: frames must be uint8 [P,B,C,84,84]")
+    logits = torch.empty((P, B, n_actions), dtype=torch.float32, device=dev)
+    actions = torch.empty((P, B), dtype=torch.int32, device=dev)
+    check(load().cev_deepqn_forward(handle(dev.index), _ptr(members), P, members.stride(0),
+                                    _ptr(frames), B, int(c_in), int(n_actions), _ptr(logits),
+                                    _ptr(actions), _stream(dev)), "cev_deepqn_forward")
+    return logits, actions
+
+
+def init_states(seed, stream_id, n, device):
+    """Device-generated initial env states fp64[n,11] (Appendix A.3 distribution)."""
+    out = torch.empty((n, _lib.INIT_STATE_DIM), dtype=torch.float64, device=device)
+    dev = out.device
+    check(load().cev_init_states_f64(handle(dev.index), int(seed), int(stream_id), n, _ptr(out),
+                                     _stream(dev)), "cev_init_states_f64")
+    return out
+
+
+def random_frames(seed, shape, device):
+    out = torch.empty(shape, dtype=torch.uint8, device=device)
+    if out.numel() % 16:
+        raise _lib.CevError("random_frames: byte count must be a multiple of 16")
+    dev = out.device
+    check(load().cev_random_frames_u8(handle(dev.index), int(seed), out.numel(), _ptr(out),
+                                      _stream(dev)), "cev_random_frames_u8")
+    return out
+
+
+def philox_words(seed, kind, role, gen, member0, n_members, n4, device):
+    out = torch.empty((n_members, n4, 4), dtype=torch.int32, device=device)
+    dev = out.device
+    check(load().cev_philox_words(handle(dev.index), int(seed), int(kind), int(role), int(gen),
+                                  int(member0), int(n_members), int(n4), _ptr(out), _stream(dev)),
+          "cev_philox_words")
+    return out
+
+
+def fp32_peak(device, mode=1):
+    """Measured FP32 FMA-pipe peak in TFLOP/s (mode 0 scalar FFMA, 1 packed FFMA2)."""
+    dev = torch.device(device)
+    val = ctypes.c_double()
+    check(load().cev_fp32_peak(handle(dev.index), int(mode), ctypes.byref(val), _stream(dev)),
+          "cev_fp32_peak")
+    return val.value

@@ -1,0 +1,206 @@
+/*
+ * coevonet_b200 -- C ABI of the B200-native population-evaluation hot path.
+ *
+ * The reference (CogSP/CoEvoNet) is pure Python and has no FFI; the drop-in
+ * boundary is its Python call surface.  This header is
+ * the native boundary underneath that surface: what a binding (ctypes / cffi /
+ * pybind) for the hot path binds.  Every entry point cites the reference
+ * function whose body it replaces.
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers owned by the caller unless a parameter is
+ *    documented as host memory.  No torch types.  The library allocates nothing
+ *    persistent except the per-handle workspace.
+ *  - Every compute call is asynchronous on `stream` and returns 0 on success,
+ *    <0 on an argument / launch error (text via cev_last_error()).
+ *  - Device-detected faults (non-finite activations, the reference's
+ *    ValueError at MPE/fcnetwork.py:39-65) are OR-ed into `*status`
+ *    (device int32, may be NULL); the caller reads it after synchronising.
+ *  - Network rows use the reference's `parameters()` order
+ *    (MPE/fcnetwork.py:11-22) with the row pitch padded
+ *    to a multiple of 32 floats: cev_fc_pitch(in_dim).
+ *  - Seats are in world / AEC order: 0 = adversary_0, 1 = agent_0, 2 = agent_1.
+ */
+#ifndef COEVONET_B200_H
+#define COEVONET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cev_handle cev_handle;
+typedef void* cev_stream;               /* cudaStream_t */
+
+#define CEV_OK 0
+#define CEV_ERR_ARG (-1)
+#define CEV_ERR_CUDA (-2)
+#define CEV_ERR_UNSUPPORTED (-3)
+
+#define CEV_STATUS_NONFINITE 1          /* MPE/fcnetwork.py:39,49,57,65 */
+
+#define CEV_SEAT_ADVERSARY 0
+#define CEV_SEAT_AGENT_0 1
+#define CEV_SEAT_AGENT_1 2
+
+#define CEV_INIT_STATE_DIM 11           /* goal, adv.xy, a0.xy, a1.xy, lm0.xy, lm1.xy */
+#define CEV_ROLLOUT_OUT_DIM 4           /* sum_good, last_good, sum_adv, min_gap */
+
+/* noise kinds (Philox counter word 3 = role | kind << 8) */
+#define CEV_KIND_ES 0
+#define CEV_KIND_GA 1
+#define CEV_KIND_ENV 2
+#define CEV_KIND_FRAMES 3
+
+int cev_version(void);
+const char* cev_last_error(void);
+int cev_create(int device, cev_handle** out);
+int cev_destroy(cev_handle* h);
+/* number of SMs / co-resident 4-CTA clusters the rollout kernel will use */
+int cev_device_info(cev_handle* h, int* n_sm, int* n_clusters);
+
+/* flat-row geometry of FCNetwork(in_dim, 5): 139781 / 138757 and padded pitch */
+int cev_fc_dim(int in_dim);
+int cev_fc_pitch(int in_dim);
+/* DeepQN(c_in, n_actions) row length (Atari/deepqn.py:7-36) and padded pitch */
+int cev_dqn_dim(int c_in, int n_actions);
+int cev_dqn_pitch(int c_in, int n_actions);
+
+typedef struct {
+    int32_t n_cycles;            /* world steps per episode: 25, or floor(limit/3)
+                                    under play_MPE's agent-step limit
+                                    (utils/game_logic_functions.py:127,195) */
+    int32_t integrate_pos_first; /* SURVEY.md Appendix A.4 switch (1 = PettingZoo >= 1.24) */
+    int32_t variant;             /* 0 auto, 1 generic kernel, 2 cluster kernel */
+    int32_t reserved;
+} cev_rollout_cfg;
+
+/*
+ * K1 -- fused MPE rollout, structured form.
+ * Replaces the evaluation loops' body: play_game / play_MPE
+ * (utils/game_logic_functions.py:123-228) + FCNetwork.forward /
+ * determine_action (MPE/fcnetwork.py:37-90) + the simple_adversary_v3 world
+ * step, for P members x K opponent sets x E env instances
+ * (genetic_algorithm.py:125-217, evolutionary_strategy.py:236-251).
+ *
+ * Member m sits in `member_seat`; the two other seats (ascending seat order)
+ * are filled by opp_a[k], opp_b[k].  init is fp64 [P,K,E,11] (or [K,E,11]
+ * shared by all members when init_shared != 0).  out is fp64 [P,K,E,4]:
+ * (sum_c r_good, r_good of the last cycle, sum_c r_adv, min top-2 logit gap).
+ */
+int cev_mpe_rollout_f32(cev_handle* h, int member_seat,
+                        const float* members, int P, int64_t member_pitch,
+                        const float* opp_a, int64_t opp_a_pitch,
+                        const float* opp_b, int64_t opp_b_pitch, int K,
+                        const double* init, int init_shared, int E,
+                        const cev_rollout_cfg* cfg,
+                        double* out, int32_t* status, cev_stream stream);
+
+/*
+ * K1 -- indexed form: N independent episodes, episode e played by rows
+ * idx[e] = (adversary_0 row, agent_0 row, agent_1 row).  The batched
+ * equivalent of N calls of play_game (utils/game_logic_functions.py:215).
+ */
+int cev_mpe_rollout_indexed_f32(cev_handle* h,
+                                const float* w_adv, int64_t adv_pitch,
+                                const float* w_a0, int64_t a0_pitch,
+                                const float* w_a1, int64_t a1_pitch,
+                                const int32_t* idx, const double* init, int N,
+                                const cev_rollout_cfg* cfg,
+                                double* out, int32_t* status, cev_stream stream);
+
+/*
+ * K3 -- GA re-population.  Replaces mutate_elites (genetic_algorithm.py:32-48)
+ * + MPEAgent.clone (MPE/mpe_agent.py:24-28) + Agent.mutate (agent.py:25-29)
+ * + "best survives unmutated" (genetic_algorithm.py:255-268).
+ * elites: fp32 [E, pitch] gathered elite rows (elite 0 = best).
+ * Rows [row0, row0+n_rows) of the NEXT population are written to `out`
+ * (local row r = global member row0 + r): global row 0 = elites[0]; global row
+ * c >= 1 = elites[(c-1) % E] + sigma * N(0,1), Philox(seed, GA, role, gen,
+ * member=c, param).  noise_out (optional) receives the N(0,1) draws.
+ */
+int cev_ga_repopulate_f32(cev_handle* h, const float* elites, int E,
+                          int D, int64_t pitch, float sigma,
+                          uint64_t seed, int role, uint32_t gen,
+                          int64_t row0, int64_t n_rows,
+                          float* out, float* noise_out, cev_stream stream);
+
+/* gather rows: dst[i] = src[idx[i]] (elite / HoF extraction, genetic_algorithm.py:240-275) */
+int cev_gather_rows_f32(cev_handle* h, const float* src, int64_t pitch,
+                        const int64_t* idx, int n, float* dst, cev_stream stream);
+
+/*
+ * K4 -- selection.  Replaces np.argsort(fitness)[::-1][:E]
+ * (genetic_algorithm.py:223-234): indices of the k largest, descending,
+ * ties -> lower index (defined; the reference's sort is unstable).
+ */
+int cev_select_topk_f64(cev_handle* h, const double* fitness, int64_t P, int k,
+                        int64_t* idx_out, cev_stream stream);
+
+/*
+ * K5 -- ES perturbation.  Replaces Agent.mutate_ES (agent.py:31-70) for
+ * members [row0, row0+n_rows): out[r] = theta + sigma * N(0,1) on Linear
+ * parameters only (LayerNorm rows copied), Philox(seed, ES, role, gen, member).
+ */
+int cev_es_perturb_f32(cev_handle* h, const float* theta, int in_dim,
+                       float sigma, uint64_t seed, int role, uint32_t gen,
+                       int64_t row0, int64_t n_rows, int64_t pitch,
+                       float* out, float* noise_out, cev_stream stream);
+
+/*
+ * K6 -- ES fitness-weighted update.  Replaces compute_weight_update
+ * (evolutionary_strategy.py:120-148): delta = lr/(n_total*sigma) *
+ * sum_i (sigma*z_i) * fitness_i over members [row0, row0+n_rows), noise
+ * regenerated from the Philox key (never read from HBM).  delta is fp32[D]
+ * in the full-row layout (zeros on LayerNorm entries); partial sums over a
+ * rank's members are all-reduced by the caller.
+ */
+int cev_es_update_f32(cev_handle* h, const double* fitness, int in_dim,
+                      float sigma, float lr, int64_t n_total,
+                      uint64_t seed, int role, uint32_t gen,
+                      int64_t row0, int64_t n_rows,
+                      float* delta, cev_stream stream);
+
+/* theta[j] += delta[j] (evolutionary_strategy.py:259-265) */
+int cev_axpy_f32(cev_handle* h, float a, const float* x, float* y, int64_t n, cev_stream stream);
+
+/*
+ * K7 -- fitness-sharing distances.  Replaces the distance loop of
+ * diversity_penalty (utils/game_logic_functions.py:12-37):
+ * d[i] = || pop[i] - ref ||_2 over the perturbable (Linear) parameters.
+ */
+int cev_diversity_dist_f32(cev_handle* h, const float* pop, int64_t n_rows,
+                           int64_t pitch, const float* ref, int in_dim,
+                           float* dist, cev_stream stream);
+
+/*
+ * K2 -- grouped per-member DeepQN forward.  Replaces DeepQN.forward
+ * (Atari/deepqn.py:39-48): frames u8 [P,B,C,84,84]; logits fp32 [P,B,A];
+ * actions int32 [P,B] (first maximum, Atari/deepqn.py:55-60).
+ */
+int cev_deepqn_forward(cev_handle* h, const float* members, int P, int64_t pitch,
+                       const uint8_t* frames, int B, int c_in, int n_actions,
+                       float* logits, int32_t* actions, cev_stream stream);
+
+/* device-side synthetic inputs (bench / tests): initial env states drawn
+ * U(-1,1)^2 + goal in {0,1} (Appendix A.3 distribution, Philox stream) and
+ * uint8 frames. */
+int cev_init_states_f64(cev_handle* h, uint64_t seed, uint32_t stream_id,
+                        int64_t n, double* out, cev_stream stream);
+int cev_random_frames_u8(cev_handle* h, uint64_t seed, int64_t n_bytes,
+                         uint8_t* out, cev_stream stream);
+/* raw Philox words for bit-exact RNG checks: out u32 [n_members, n4, 4] */
+int cev_philox_words(cev_handle* h, uint64_t seed, int kind, int role, uint32_t gen,
+                     int64_t member0, int64_t n_members, int64_t n4,
+                     uint32_t* out, cev_stream stream);
+
+/* FP32 FMA-pipe peak micro-benchmark (the FP32 roofline
+ * denominator is measured, not assumed).  Returns achieved TFLOP/s in *tflops
+ * (host pointer); mode 0 = scalar FFMA, 1 = packed FFMA2. */
+int cev_fp32_peak(cev_handle* h, int mode, double* tflops, cev_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COEVONET_B200_H */

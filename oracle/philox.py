@@ -97,3 +97,20 @@ def words(seed, kind, role, gen, members, n4):
     j4 = np.arange(n4, dtype=np.uint32).reshape(1, -1)
     tag = np.uint32((int(role) & 0xFF) | (int(kind) << 8))
     return np.stack(philox4x32_10(j4, members, np.uint32(gen), tag, k0, k1), axis=-1)
+
+
+def init_states(seed, stream_id, n):
+    """fp64[n,11] synthetic initial env states, bit-exact restatement of the
+    device generator (``cev_init_states_f64``): goal = word0 & 1, the ten
+    coordinates U(-1,1) from words 1..10 of three Philox blocks per record."""
+    k0, k1 = split_seed(seed)
+    rec = np.arange(n, dtype=np.uint32)
+    tag = np.uint32(KIND_ENV << 8)
+    w = []
+    for b in range(3):
+        w.extend(philox4x32_10(np.uint32(b), rec, np.uint32(stream_id), tag, k0, k1))
+    out = np.zeros((n, 11))
+    out[:, 0] = (w[0] & np.uint32(1)).astype(np.float64)
+    for i in range(10):
+        out[:, 1 + i] = (w[1 + i].astype(np.float64) + 0.5) * (2.0 / 4294967296.0) - 1.0
+    return out
