@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""Bench of the population-evaluation hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this build, N GPUs of one node
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (port)
+
+Workload (BASELINE.json configs[1]): Co-ES on simple_adversary_v3, 1024 members
+per GPU x 16 env instances x 3 roles, 25-cycle episodes, Philox seed-regenerated
+noise.  One "step" = one Co-ES generation of the hot path:
+for each role  K5 perturb -> K1 fused rollout -> fitness -> K6 update (+ the
+fitness all-gather and delta all-reduce when N > 1), then the 10 evaluation
+games.  `value` = world-steps/s over all ranks (1 world step = one physics
+step = 3 agent `env.step` calls of the AEC reference); weak scaling (1024
+members per GPU).  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+P_PER_GPU = 1024
+ENVS = 16
+CYCLES = 25
+FLOP_PER_WORLD_STEP = 822784          # three MLP forwards, SURVEY.md section 8d
+ROLES = ("agent_0", "agent_1", "adversary_0")
+METRIC = "mpe_env_steps_per_sec"
+UNIT = "world-steps/s"
+
+
+def _args_bag(P):
+    return types.SimpleNamespace(
+        algorithm="ES", generations=1, population=P, hof_size=1, game="simple_adversary_v3",
+        mutation_power_agent_0=0.05, mutation_power_agent_1=0.05, mutation_power_adversary=0.05,
+        learning_rate=0.1, max_timesteps_per_episode=400, max_evaluation_steps=400, elites_number=2,
+        adaptive=False, max_mutation_power=0.5, min_mutation_power=0.001, fitness_sharing=False,
+        early_stopping=False, patience=300, min_delta=0.1, debug=False, precision="float32",
+        save=False, envs_per_member=ENVS, reference_compat=True, init_states="device",
+        seed=1870300, plots=False, record_history=False)
+
+
+def _config(n_gpus):
+    return {"workload": "Co-ES simple_adversary_v3 population evaluation (BASELINE configs[1])",
+            "population_per_gpu": P_PER_GPU, "population": P_PER_GPU * n_gpus, "envs_per_member": ENVS,
+            "roles": 3, "cycles_per_episode": CYCLES, "noise": "Philox4x32-10 regenerated from seed",
+            "step": "one generation: 3 x (perturb, rollout, update) + 10 eval games",
+            "env_step_definition": "world step (3 agent env.step calls); agent-steps/s = 3 x value",
+            "cache": "inputs larger than L2 (3 x 1024 member rows = 1.7 GB per GPU vs 126 MB L2)",
+            "parallelism": f"population sharded over {n_gpus} GPU(s)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                power.append(float(r[3]))
+                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                                  ("sw_power_cap", 8)):
+                    if r[col].lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def _measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def _k1_traffic():
+    """DRAM bytes per K1 launch from the committed ncu capture (profiles/), or null."""
+    path = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            return json.load(f)
+    return None
+
+
+# ---------------------------------------------------------------------------
+# CPU baseline legs (the oracle as the timed baseline -- never on the product path)
+# ---------------------------------------------------------------------------
+def _cpu_sample(n_episodes, n_procs):
+    import numpy as np
+    from oracle import mpe_env, serial_port, weights
+    rows = {"agent_0": weights.make_fc_rows(1, 10, 1)[0], "agent_1": weights.make_fc_rows(1, 10, 2)[0],
+            "adversary_0": weights.make_fc_rows(1, 8, 3)[0]}
+    init = mpe_env.draw_initial_states(n_episodes)
+    _, wall = serial_port.timed_sample(rows, init, n_procs)
+    return n_episodes * CYCLES / wall, wall
+
+
+def cpu_baseline_block(budget_s=12.0):
+    """Episode-serial port on ONE core (how the reference runs), bounded sample."""
+    rate, _ = _cpu_sample(16, 1)                       # calibrate
+    n = max(32, min(4096, int(budget_s * rate / CYCLES)))
+    value, wall = _cpu_sample(n, 1)
+    return {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{n} episodes of the same workload (batch-1 torch forward + AEC numpy env, "
+                      f"oracle/serial_port.py) in {wall:.1f} s; the reference is single-process"}
+
+
+def run_reference_arm(ns):
+    """The reference's CPU implementation of the path (port; /root/reference does not
+    travel to the GPU box), all host cores, each step a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    rate1, _ = _cpu_sample(8, 1)
+    per_step = max(cores * 4, min(cores * 64, int(6.0 * rate1 * cores / CYCLES)))
+    for _ in range(ns.warmup):
+        _cpu_sample(max(cores, per_step // 4), cores)
+    t0 = time.perf_counter()
+    for _ in range(ns.steps):
+        _cpu_sample(per_step, cores)
+    wall = time.perf_counter() - t0
+    value = ns.steps * per_step * CYCLES / wall
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ns.gpus,
+            "steps": ns.steps, "warmup": ns.warmup, "ms_per_step": wall / ns.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": _config(ns.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{per_step} episodes per step over {cores} processes "
+                                       "(oracle/serial_port.py: episode-serial batch-1 port of the reference path)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def run_gpu_arm(ns):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from coevonet_b200 import engine, layout, ops
+    from coevonet_b200.MPE.fcnetwork import FCNetwork
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != ns.gpus:
+        if world == 1 and ns.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    comm = engine.Comm()
+
+    P = P_PER_GPU * world
+    args = _args_bag(P)
+    torch.manual_seed(0)
+    theta = {r: FCNetwork(layout.OBS_DIM[r], 5, "float32").flat_row() for r in ROLES}
+    eng = engine.ESEngine(args, dev, theta, comm=comm)
+    n_local = eng.shard.n_local
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput (`value`) --------------------------------
+    for _ in range(ns.warmup):
+        eng.step()
+    barrier()
+    eng.k1_events = []
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ops.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(ns.steps):
+        eng.step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ops.launch_count - launches0
+    ms_total = e0.elapsed_time(e1)
+    k1_ms = [a.elapsed_time(b) for a, b in eng.k1_events]
+    eng.k1_events = None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    steps_per_gen = (P * ENVS * 3 + engine.N_EVAL_GAMES) * CYCLES
+    value = steps_per_gen * ns.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the host-buffer API (`e2e`) --------------------------
+    # inputs of a generation live in pinned host memory (base rows + initial env states, as the
+    # reference's host-side env would supply them); results (fitness, updated rows) are read back
+    init_host = {r: torch.empty((n_local, 1, ENVS, 11), dtype=torch.float64).pin_memory() for r in ROLES}
+    gen_states = ops.init_states(1870300, 0x7000, n_local * ENVS * 3, dev).reshape(3, n_local, 1, ENVS, 11).cpu()
+    for i, r in enumerate(ROLES):
+        init_host[r].copy_(gen_states[i])
+    theta_host = {r: eng.theta[r].cpu().pin_memory() for r in ROLES}
+    fit_host = {r: torch.empty(n_local, dtype=torch.float64).pin_memory() for r in ROLES}
+
+    def e2e_step():
+        for r in ROLES:
+            eng.theta[r].copy_(theta_host[r], non_blocking=True)
+        init_dev = {r: init_host[r].to(dev, non_blocking=True) for r in ROLES}
+        eng.step(init_by_role=init_dev)
+        for r in ROLES:
+            fit_host[r].copy_(eng.rewards[r], non_blocking=True)
+            theta_host[r].copy_(eng.theta[r], non_blocking=True)
+        torch.cuda.synchronize()
+
+    h2d = sum(init_host[r].numel() * 8 + theta_host[r].numel() * 4 for r in ROLES)
+    d2h = sum(fit_host[r].numel() * 8 + theta_host[r].numel() * 4 for r in ROLES)
+    e2e_steps = max(1, min(ns.steps, 5))
+    e2e_step()
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    g1.record()
+    barrier()
+    e2e_ms = g0.elapsed_time(g1)          # device clock; the per-step host waits fall inside the bracket
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = steps_per_gen * e2e_steps / (float(t.item()) * 1e-3)
+
+    if rank == 0:
+        peaks, peaks_src = _measured_peaks()
+        fp32_peak = max(ops.fp32_peak(dev, 0), ops.fp32_peak(dev, 1))
+        k1_avg_ms = float(np.mean(k1_ms))
+        k1_flop = n_local * ENVS * CYCLES * FLOP_PER_WORLD_STEP
+        achieved = k1_flop / (k1_avg_ms * 1e-3) / 1e12
+        traffic = _k1_traffic()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": ns.steps,
+            "warmup": ns.warmup, "ms_per_step": ms_total / ns.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": _config(world),
+            "agent_steps_per_sec": 3 * value,
+            "roofline": {
+                "kernel": "rollout_cluster_kernel<16> (K1)", "bound": "fp32",
+                "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+                "peak_source": "FP32 FMA-pipe peak measured live by cev_fp32_peak (SURVEY.md 8d: "
+                               "K1 is bound by the FP32 pipe; MEASURED_PEAKS.json has no FP32 figure)",
+                "frac_of_bf16_tensor_peak": achieved / peaks["bf16_tflops"],
+                "tensor_peak_source": f"MEASURED_PEAKS.json bf16_tflops ({peaks_src})",
+                "k1_ms_per_launch": k1_avg_ms, "k1_launches_timed": len(k1_ms),
+                "k1_share_of_step": sum(k1_ms) / ms_total if world == 1 else None,
+                "algorithmic_flop_per_launch": k1_flop,
+                "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                "traffic_source": traffic["source"] if traffic else None},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        if world == 1 and not ns.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_block()
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ns = ap.parse_args()
+    if ns.impl == "reference":
+        return run_reference_arm(ns)
+    return run_gpu_arm(ns)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

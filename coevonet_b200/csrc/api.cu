@@ -182,4 +182,14 @@ int cev_mpe_rollout_indexed_f32(cev_handle* h, const float* w_adv, int64_t adv_p
     return launch_rollout_generic(h, g, (cudaStream_t)stream);
 }
 
+int cev_fc_forward_f32(cev_handle* h, const float* rows, int64_t pitch, int in_dim, const int32_t* idx,
+                       const float* obs, int64_t N, float* logits, int32_t* actions, int32_t* status,
+                       cev_stream stream) {
+    CEV_REQUIRE(h && rows && obs && logits, "fc_forward: null pointer");
+    CEV_REQUIRE(in_dim == IN_ADV || in_dim == IN_GOOD, "fc_forward: in_dim must be 8 or 10");
+    CEV_REQUIRE(pitch >= fc_offsets(in_dim).total && pitch % 4 == 0 && aligned16(rows),
+                "fc_forward: bad pitch / alignment");
+    return launch_fc_forward(h, rows, pitch, in_dim, idx, obs, N, logits, actions, status, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -230,9 +230,10 @@ __device__ __forceinline__ double u_pm1(uint32_t x) {
 }
 
 __global__ void __launch_bounds__(PT) init_states_kernel(uint32_t k0, uint32_t k1, uint32_t stream_id,
-                                                         int64_t n, double* __restrict__ out) {
-    const int64_t r = (int64_t)blockIdx.x * PT + threadIdx.x;
-    if (r >= n) return;
+                                                         int64_t rec0, int64_t n, double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * PT + threadIdx.x;
+    if (i >= n) return;
+    const int64_t r = rec0 + i;
     const uint32_t tag = noise_tag(CEV_KIND_ENV, 0);
     uint32_t w[12];
 #pragma unroll
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(PT) init_states_kernel(uint32_t k0, uint32_t k
         const U4 v = philox4x32_10(U4{(uint32_t)b, (uint32_t)r, stream_id, tag}, k0, k1);
         w[4 * b] = v.x; w[4 * b + 1] = v.y; w[4 * b + 2] = v.z; w[4 * b + 3] = v.w;
     }
-    double* o = out + r * CEV_INIT_STATE_DIM;
+    double* o = out + i * CEV_INIT_STATE_DIM;
     o[0] = (double)(w[0] & 1u);
 #pragma unroll
     for (int i = 0; i < 10; ++i) o[1 + i] = u_pm1(w[1 + i]);
@@ -408,13 +409,14 @@ int cev_diversity_dist_f32(cev_handle* h, const float* pop, int64_t n_rows, int6
     return check_cuda(cudaGetLastError(), "diversity_dist_kernel");
 }
 
-int cev_init_states_f64(cev_handle* h, uint64_t seed, uint32_t stream_id, int64_t n, double* out,
+int cev_init_states_f64(cev_handle* h, uint64_t seed, uint32_t stream_id, int64_t rec0, int64_t n, double* out,
                         cev_stream stream) {
-    CEV_REQUIRE(h && out && n >= 0 && n <= 0xFFFFFFFFll, "init_states: bad arguments");
+    CEV_REQUIRE(h && out && n >= 0 && rec0 >= 0 && rec0 + n <= 0xFFFFFFFFll, "init_states: bad arguments");
     if (n == 0) return CEV_OK;
     uint32_t k0, k1;
     split_seed(seed, k0, k1);
-    init_states_kernel<<<(unsigned)((n + PT - 1) / PT), PT, 0, (cudaStream_t)stream>>>(k0, k1, stream_id, n, out);
+    init_states_kernel<<<(unsigned)((n + PT - 1) / PT), PT, 0, (cudaStream_t)stream>>>(k0, k1, stream_id, rec0, n,
+                                                                                       out);
     return check_cuda(cudaGetLastError(), "init_states_kernel");
 }
 

@@ -176,4 +176,57 @@ int launch_rollout_generic(cev_handle* h, const GenericParams& p, cudaStream_t s
     return check_cuda(cudaGetLastError(), "rollout_generic_kernel launch");
 }
 
+// Batched FCNetwork.forward on arbitrary observations (function-level op for
+// logits parity under teacher forcing and for the FCNetwork.forward drop-in):
+// one CTA per (row idx[n], obs[n]) pair.
+__global__ void __launch_bounds__(GEN_THREADS) fc_forward_kernel(const float* __restrict__ W, int64_t pitch,
+                                                                int in_dim, const int32_t* __restrict__ idx,
+                                                                const float* __restrict__ obs_in, int64_t N,
+                                                                float* __restrict__ logits,
+                                                                int32_t* __restrict__ actions,
+                                                                int32_t* status) {
+    __shared__ __align__(16) float h1[H1];
+    __shared__ __align__(16) float h2[H2];
+    __shared__ float red[GEN_WARPS];
+    __shared__ float obs[12];
+    __shared__ float lgs[NACT];
+    __shared__ int nonfinite;
+    for (int64_t n = blockIdx.x; n < N; n += gridDim.x) {
+        if (threadIdx.x == 0) nonfinite = 0;
+        if (threadIdx.x < in_dim) {
+            const float v = obs_in[n * in_dim + threadIdx.x];
+            obs[threadIdx.x] = v;
+            if (!isfinite(v)) nonfinite = 1;
+        }
+        __syncthreads();
+        const float* Wr = W + (int64_t)(idx ? idx[n] : 0) * pitch;
+        fc_forward_one(Wr, in_dim, obs, h1, h2, red, lgs, &nonfinite);
+        if (threadIdx.x == 0) {
+            float lg[NACT];
+            bool fin = true;
+#pragma unroll
+            for (int a = 0; a < NACT; ++a) {
+                lg[a] = lgs[a];
+                logits[n * NACT + a] = lg[a];
+                fin = fin && isfinite(lg[a]);
+            }
+            float gap;
+            const int act = argmax_first5(lg, gap);
+            if (actions) actions[n] = act;
+            if ((!fin || nonfinite) && status) atomicOr(status, CEV_STATUS_NONFINITE);
+        }
+        __syncthreads();
+    }
+}
+
+int launch_fc_forward(cev_handle* h, const float* W, int64_t pitch, int in_dim, const int32_t* idx,
+                      const float* obs, int64_t N, float* logits, int32_t* actions, int32_t* status,
+                      cudaStream_t stream) {
+    if (N <= 0) return CEV_OK;
+    const int64_t max_grid = (int64_t)h->n_sm * 8;
+    const int grid = (int)(N < max_grid ? N : max_grid);
+    fc_forward_kernel<<<grid, GEN_THREADS, 0, stream>>>(W, pitch, in_dim, idx, obs, N, logits, actions, status);
+    return check_cuda(cudaGetLastError(), "fc_forward_kernel launch");
+}
+
 }  // namespace cev

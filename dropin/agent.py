@@ -1,0 +1,1 @@
+from coevonet_b200.agent import *  # noqa: F401,F403  (drop-in shim: same top-level module name as the reference)

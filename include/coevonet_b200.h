@@ -111,6 +111,17 @@ int cev_mpe_rollout_indexed_f32(cev_handle* h,
                                 double* out, int32_t* status, cev_stream stream);
 
 /*
+ * Function-level op: batched FCNetwork.forward + determine_action
+ * (MPE/fcnetwork.py:37-90) on caller-supplied observations: sample n uses row
+ * idx[n] (row 0 when idx is NULL) and obs[n, 0..in_dim).  logits fp32 [N,5],
+ * actions int32 [N] (optional).  Used for logits parity under teacher forcing
+ * and by the FCNetwork.forward drop-in.
+ */
+int cev_fc_forward_f32(cev_handle* h, const float* rows, int64_t pitch, int in_dim,
+                       const int32_t* idx, const float* obs, int64_t N,
+                       float* logits, int32_t* actions, int32_t* status, cev_stream stream);
+
+/*
  * K3 -- GA re-population.  Replaces mutate_elites (genetic_algorithm.py:32-48)
  * + MPEAgent.clone (MPE/mpe_agent.py:24-28) + Agent.mutate (agent.py:25-29)
  * + "best survives unmutated" (genetic_algorithm.py:255-268).
@@ -184,10 +195,11 @@ int cev_deepqn_forward(cev_handle* h, const float* members, int P, int64_t pitch
                        float* logits, int32_t* actions, cev_stream stream);
 
 /* device-side synthetic inputs (bench / tests): initial env states drawn
- * U(-1,1)^2 + goal in {0,1} (Appendix A.3 distribution, Philox stream) and
- * uint8 frames. */
+ * U(-1,1)^2 + goal in {0,1} (Appendix A.3 distribution, Philox stream; records
+ * rec0 .. rec0+n-1 of stream `stream_id`, so shards generate their own slice)
+ * and uint8 frames. */
 int cev_init_states_f64(cev_handle* h, uint64_t seed, uint32_t stream_id,
-                        int64_t n, double* out, cev_stream stream);
+                        int64_t rec0, int64_t n, double* out, cev_stream stream);
 int cev_random_frames_u8(cev_handle* h, uint64_t seed, int64_t n_bytes,
                          uint8_t* out, cev_stream stream);
 /* raw Philox words for bit-exact RNG checks: out u32 [n_members, n4, 4] */

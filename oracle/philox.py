@@ -99,12 +99,12 @@ def words(seed, kind, role, gen, members, n4):
     return np.stack(philox4x32_10(j4, members, np.uint32(gen), tag, k0, k1), axis=-1)
 
 
-def init_states(seed, stream_id, n):
+def init_states(seed, stream_id, n, rec0=0):
     """fp64[n,11] synthetic initial env states, bit-exact restatement of the
     device generator (``cev_init_states_f64``): goal = word0 & 1, the ten
     coordinates U(-1,1) from words 1..10 of three Philox blocks per record."""
     k0, k1 = split_seed(seed)
-    rec = np.arange(n, dtype=np.uint32)
+    rec = np.arange(rec0, rec0 + n, dtype=np.uint32)
     tag = np.uint32(KIND_ENV << 8)
     w = []
     for b in range(3):

@@ -1,0 +1,166 @@
+"""Drop-in drivers on the GPU against golden runs of the UNMODIFIED reference
+drivers (tests/golden/ga_run.npz, es_run.npz; oracle/make_golden_drivers.py).
+
+Both runs start from the same ``torch.manual_seed`` founders, consume the same
+host initial-state stream and use the same Philox noise (the golden run had it
+injected into the reference's ``torch.normal`` / ``np.random.normal``).  A
+generation is compared member by member; because one forked trajectory (an
+argmax decided by a ~1e-7 logit gap) changes selection / the update and with it
+every later generation, later generations are only compared while all earlier
+ones agreed.
+"""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROLES = ("agent_0", "agent_1", "adversary_0")
+RTOL = 1e-4
+
+
+def _args(**kw):
+    a = types.SimpleNamespace(
+        algorithm="GA", generations=2, population=6, hof_size=2, game="simple_adversary_v3",
+        mutation_power_agent_0=0.005, mutation_power_agent_1=0.05, mutation_power_adversary=0.05,
+        learning_rate=0.1, max_timesteps_per_episode=400, max_evaluation_steps=400, elites_number=2,
+        adaptive=True, max_mutation_power=0.7, min_mutation_power=0.0001, fitness_sharing=True,
+        early_stopping=False, patience=300, min_delta=0.1, debug=False, train=True, test=False,
+        render=False, env_mode="AEC", precision="float32", save=False, play_against_yourself=False,
+        average_window=50, envs_per_member=1, reference_compat=True, init_states="reference",
+        seed=1870300, plots=False, record_history=True)
+    a.__dict__.update(kw)
+    return a
+
+
+def _close(a, b):
+    return np.abs(a - b) <= RTOL * np.maximum(1.0, np.abs(b))
+
+
+def test_ga_train_matches_reference_run(golden, tmp_path):
+    from coevonet_b200.genetic_algorithm import genetic_algorithm_train
+    from coevonet_b200.utils.game_logic_functions import initialize_env
+    g = golden("ga_run")
+    gens = int(g["gens"])
+    args = _args(population=int(g["P"]), hof_size=int(g["hof"]), elites_number=int(g["elites"]),
+                 generations=gens, max_mutation_power=float(g["max_sigma"]),
+                 min_mutation_power=float(g["min_sigma"]))
+    torch.manual_seed(int(g["torch_seed"]))
+    env = initialize_env(args)
+    genetic_algorithm_train(env, env.agents[0], args, str(tmp_path))
+    hist = args._ga_engine.history
+    assert len(hist) == gens
+    agreed = 0
+    for gen in range(gens):
+        ok = True
+        for ri, role in enumerate(ROLES):
+            want = g["fitness"][gen, ri]
+            got = hist[gen]["fitness"][role]
+            match = _close(got, want)
+            if gen == 0:
+                assert match.sum() >= len(want) - 1, f"gen0 {role}: {got} vs {want}"
+            ok = ok and match.all()
+            assert abs(hist[gen]["diversity"][role] - g["diversity"][gen, ri]) <= 1e-3 * max(1, abs(g["diversity"][gen, ri])) or not ok
+            if match.all():
+                want_ids = np.argsort(-want, kind="stable")[:args.elites_number]
+                assert np.array_equal(hist[gen]["elite_ids"][role], want_ids)
+        if not ok:
+            break
+        np.testing.assert_allclose(hist[gen]["evals"], g["evals"][gen], rtol=RTOL, atol=1e-9)
+        np.testing.assert_allclose([hist[gen]["sigma"][r] for r in ROLES], g["sigma_used"][gen], rtol=1e-12)
+        agreed += 1
+    assert agreed >= 1, "not even generation 0 agreed with the reference run"
+    print(f"GA: {agreed}/{gens} generations agree with the reference run")
+    if agreed == gens:
+        got_sigma = [args.mutation_power_agent_0, args.mutation_power_agent_1, args.mutation_power_adversary]
+        np.testing.assert_allclose(got_sigma, g["final_sigma"], rtol=1e-12)
+
+
+def test_es_train_matches_reference_run(golden, tmp_path):
+    from coevonet_b200 import layout
+    from coevonet_b200.evolutionary_strategy import evolution_strategy_train
+    from coevonet_b200.utils.game_logic_functions import initialize_env
+    g = golden("es_run")
+    gens = int(g["gens"])
+    args = _args(algorithm="ES", population=int(g["P"]), hof_size=1, generations=gens,
+                 mutation_power_agent_0=float(g["sigma0"]), mutation_power_agent_1=float(g["sigma0"]),
+                 mutation_power_adversary=float(g["sigma0"]), learning_rate=float(g["lr"]),
+                 max_mutation_power=float(g["max_sigma"]), min_mutation_power=float(g["min_sigma"]))
+    torch.manual_seed(int(g["torch_seed"]))
+    env = initialize_env(args)
+    a0, a1, adv = evolution_strategy_train(env, args, str(tmp_path))
+    hist = args._es_engine.history
+    agreed = 0
+    for gen in range(gens):
+        ok = True
+        for ri, role in enumerate(ROLES):
+            want = g["rewards"][gen, ri]
+            got = hist[gen]["rewards"][role]
+            match = _close(got, want)
+            if gen == 0:
+                assert match.sum() >= len(want) - 1, f"gen0 {role}: {got} vs {want}"
+            ok = ok and match.all()
+        if not ok:
+            break
+        for ri, role in enumerate(ROLES):
+            pidx = layout.fc_perturbable_index(layout.OBS_DIM[role])
+            d = hist[gen]["delta"][role][pidx]
+            assert abs(np.linalg.norm(d) - g["update_norm"][gen, ri]) <= 1e-3 * g["update_norm"][gen, ri]
+            np.testing.assert_allclose(d[:256], g["update_head"][gen, ri], rtol=0,
+                                       atol=1e-3 * np.abs(g["update_head"][gen, ri]).max())
+            assert abs(hist[gen]["diversity"][role] - g["diversity"][gen, ri]) <= 1e-3 * max(1, g["diversity"][gen, ri])
+        np.testing.assert_allclose(hist[gen]["evals"], g["evals"][gen], rtol=RTOL, atol=1e-9)
+        agreed += 1
+    assert agreed >= 1, "not even generation 0 agreed with the reference run"
+    print(f"ES: {agreed}/{gens} generations agree with the reference run")
+    if agreed == gens:
+        for ri, m in enumerate((a0, a1, adv)):
+            w = m.model.get_perturbable_weights()
+            np.testing.assert_allclose(w[:256], g["final_head"][ri], rtol=0, atol=1e-5)
+
+
+def test_play_game_and_helpers_dropin():
+    """Reference-style calls on single agents: create_agent / play_game /
+    evaluate_current_weights / mutate / mutate_ES / compute_weight_update."""
+    from coevonet_b200 import evolutionary_strategy as es
+    from coevonet_b200 import genetic_algorithm as ga
+    from coevonet_b200.utils.game_logic_functions import create_agent, initialize_env, play_game
+    from oracle import mpe_env, rollout as orollout, layout as olayout
+    args = _args()
+    torch.manual_seed(7)
+    env = initialize_env(args)
+    agents = {r: create_agent(env, args, r) for r in ROLES}
+    got = play_game(env, agents["agent_0"].model, agents["agent_1"].model, agents["adversary_0"].model, args)
+    nets = {r: olayout.pack_fc_state_dict(agents[r].model.state_dict(), olayout.OBS_DIM[r])[None] for r in ROLES}
+    init = mpe_env.draw_initial_states(2)[1:]                    # reset #1 (reset #0 = initialize_env)
+    ref = orollout.rollout(nets, np.zeros((1, 3), int), init)
+    want = [s[0] for s in orollout.compat_slots(ref)]
+    if ref["min_gap"][0] > 1e-4:
+        np.testing.assert_allclose(got, want, rtol=RTOL)
+    # forward / determine_action on the kernel
+    obs = np.linspace(-1, 1, 10).astype(np.float32)
+    logits = agents["agent_0"].model.forward(torch.from_numpy(obs), args)
+    want_lg = orollout.fc_forward(nets["agent_0"][0], obs[None], 10)[0]
+    np.testing.assert_allclose(logits.numpy(), want_lg, rtol=0, atol=2e-6)
+    assert agents["agent_0"].model.determine_action(torch.from_numpy(obs), args) == int(np.argmax(want_lg))
+    # mutation helpers change exactly what the reference changes
+    before = agents["agent_0"].model.flat_row().clone()
+    noise = agents["agent_0"].mutate_ES(args, "agent_0", 0, [], [], [])
+    after = agents["agent_0"].model.flat_row()
+    pidx = olayout.fc_perturbable_index(10)
+    np.testing.assert_allclose((after - before).numpy()[pidx], noise, rtol=0, atol=1e-6)
+    mask = np.ones(olayout.fc_dim(10), bool)
+    mask[pidx] = False
+    assert torch.equal(after[:olayout.fc_dim(10)][torch.from_numpy(mask)], before[:olayout.fc_dim(10)][torch.from_numpy(mask)])
+    agents["agent_1"].mutate(0.05)
+    kids = ga.mutate_elites(env, [agents["agent_0"], agents["agent_1"]], _args(population=5, elites_number=2), "agent_0")
+    assert len(kids) == 4
+    ev = ga.evaluate_current_weights(agents["agent_0"], agents["agent_1"], agents["adversary_0"], env, args)
+    assert len(ev) == 3 and ev[0] == ev[2]                       # rotated attribution (Appendix B)
+    upd, div = es.compute_weight_update([noise.astype(np.float32)] * 3, [1.0, 2.0, 3.0], args, "agent_0",
+                                        individual_weights=before.numpy()[pidx],
+                                        population_weights=[after.numpy()[pidx]] * 3)
+    want_upd = (0.1 / (3 * args.mutation_power_agent_0)) * noise.astype(np.float32) * 6.0 / (1 + div)
+    np.testing.assert_allclose(upd, want_upd, rtol=1e-4, atol=1e-7)

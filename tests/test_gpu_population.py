@@ -39,6 +39,8 @@ def test_init_states_bit_exact():
     assert np.array_equal(got, want)
     assert set(np.unique(got[:, 0])) == {0.0, 1.0}
     assert np.all(np.abs(got[:, 1:]) < 1.0)
+    part = ops.init_states(SEED, 3, 100, "cuda", rec0=400).cpu().numpy()
+    assert np.array_equal(part, want[400:500])
 
 
 @pytest.mark.parametrize("role,in_dim", [("agent_0", 10), ("adversary_0", 8)])
