@@ -51,6 +51,8 @@ int cev_create(int device, cev_handle** out) {
     h->n_sm = prop.multiProcessorCount;
     h->workspace = nullptr;
     h->workspace_bytes = 0;
+    h->opp_workspace = nullptr;
+    h->opp_workspace_bytes = 0;
     int ncl = rollout_cluster_max_clusters(device);
     if (ncl <= 0) ncl = h->n_sm / 4 - 4;
     h->n_clusters = ncl;
@@ -61,6 +63,7 @@ int cev_create(int device, cev_handle** out) {
 int cev_destroy(cev_handle* h) {
     if (!h) return CEV_OK;
     if (h->workspace) cudaFree(h->workspace);
+    if (h->opp_workspace) cudaFree(h->opp_workspace);
     delete h;
     return CEV_OK;
 }

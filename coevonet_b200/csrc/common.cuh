@@ -234,6 +234,8 @@ struct cev_handle {
     int n_clusters;        // co-resident 4-CTA clusters of the rollout kernel
     void* workspace;       // device scratch
     size_t workspace_bytes;
+    void* opp_workspace;   // packed opponent fc2 matrices of the rollout kernel
+    size_t opp_workspace_bytes;
 };
 
 // ---------------------------------------------------------------------------
@@ -258,6 +260,7 @@ struct ClusterParams {
     int P;
     const float* opp[2];          // the two non-member seats, ascending seat order
     int64_t opp_pitch[2];
+    const float4* opp_packed[2];  // their fc2 matrices repacked into stage images (workspace)
     int K;
     int member_seat;
     const double* init;

@@ -34,6 +34,28 @@ namespace cg = cooperative_groups;
 #define CEV_USE_FFMA2 1
 #endif
 
+#ifdef CEV_PROFILE
+// development-only phase timers (thread 0 of the first CTA): cycles per phase
+__device__ unsigned long long cev_prof_acc[16];
+__device__ int cev_debug_flags;     // bit0: do not wait for streamed data; bit1: no copies at all
+#define DBG_FLAG(b) (dbg_flags & (b))
+#define DBG_LOAD const int dbg_flags = cev_debug_flags;
+#define PROF_DECL long long _pt = clock64();
+#define PROF(i)                                                     \
+    do {                                                            \
+        if (threadIdx.x == 0 && blockIdx.x == 0) {                  \
+            const long long _n = clock64();                         \
+            cev_prof_acc[i] += (unsigned long long)(_n - _pt);      \
+            _pt = _n;                                               \
+        }                                                           \
+    } while (0)
+#else
+#define PROF_DECL
+#define PROF(i)
+#define DBG_FLAG(b) 0
+#define DBG_LOAD
+#endif
+
 namespace cev {
 
 constexpr int CL = 4;                       // CTAs per cluster
@@ -42,7 +64,8 @@ constexpr int NW = CT / 32;                 // warps per CTA
 constexpr int ROWS_Q = H2 / CL;             // fc2 rows per CTA (64)
 constexpr int KCH = 32;                     // k per streamed chunk
 constexpr int NCHUNK = H1 / KCH;            // 16
-constexpr int NSTAGE = 3;
+constexpr int NSTAGE = 3;                   // dedicated 8 KB stages (region `stage`)
+constexpr int NSTAGE_ALL = 6;               // + 3 stages borrowed from the W1 arena during a streamed pass
 constexpr int STAGE_F4 = ROWS_Q * KCH / 4;  // float4 per stage (512)
 constexpr int W1A_FLOATS = H1 * IN_GOOD + 3 * H1;   // fc1.W | fc1.b | ln1.g | ln1.b
 constexpr int SMALL_FLOATS = 512;           // b2[64] g2[64] be2[64] w3[5][64]
@@ -60,7 +83,8 @@ struct SmemLayout {
     static constexpr size_t off_plog = off_lnx + (size_t)3 * CL * BT * 8;
     static constexpr size_t off_act = off_plog + (size_t)3 * CL * NACT * BT * 4;
     static constexpr size_t off_flag = off_act + (size_t)3 * BT * 8;
-    static constexpr size_t total = off_flag + 16;
+    static constexpr size_t off_bar = off_flag + 16;             // full[6], empty[6], w1_full
+    static constexpr size_t total = off_bar + 128;
 };
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
@@ -90,66 +114,109 @@ __device__ __forceinline__ float group_sum(float v) {
 // ---------------------------------------------------------------------------
 // Layer 1 + LayerNorm + ReLU for all BT env instances (every CTA computes all
 // 512 rows: K <= 10 makes redundancy cheaper than a DSMEM all-gather).
-// Thread (e = t % BT, g = t / BT) owns rows g + G*i, i < 2*BT.
-// Output: h1p[(k>>1)*(2*BT) + 2*e + (k&1)]  (k-pair interleaved for FFMA2).
+// Thread (ep = t % (BT/2), g = t / (BT/2)) owns env pair (2ep, 2ep+1) and the
+// row PAIRS g + G*i: two adjacent rows share 128-bit weight loads, two envs
+// share every weight, and the output quad (2 rows x 2 envs) is one 128-bit store
+// into the k-pair interleaved layout  h1p[(k>>1)*(2*BT) + 2*e + (k&1)].
 // ---------------------------------------------------------------------------
 template <int BT, int IN>
 __device__ __forceinline__ void layer1(const float* __restrict__ w1a, const float* __restrict__ obs_seat,
                                        float* __restrict__ h1p, float* __restrict__ red1,
                                        int* flag) {
-    constexpr int G = CT / BT;          // row groups
-    constexpr int R1 = H1 / G;          // rows per thread (2*BT)
-    const int t = threadIdx.x, e = t % BT, g = t / BT, warp = t >> 5;
+    constexpr int NEP = BT / 2;             // env pairs
+    constexpr int G = CT / NEP;             // row-pair groups
+    constexpr int NP = (H1 / 2) / G;        // row pairs per thread
+    constexpr int NV = 2 * IN / 4;          // float4 per row pair of fc1.W
+    const int t = threadIdx.x, ep = t % NEP, g = t / NEP, warp = t >> 5, lane = t & 31;
     const float* fc1w = w1a;
     const float* fc1b = w1a + H1 * IN;
     const float* ln1g = fc1b + H1;
     const float* ln1b = ln1g + H1;
 
-    float2 ob[IN / 2];
+    float2 ob[2][IN / 2];
 #pragma unroll
-    for (int k = 0; k < IN / 2; ++k) ob[k] = *reinterpret_cast<const float2*>(obs_seat + e * 12 + 2 * k);
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int k = 0; k < IN / 2; ++k)
+            ob[j][k] = *reinterpret_cast<const float2*>(obs_seat + (2 * ep + j) * 12 + 2 * k);
 
-    float pre[R1];
-    float lsum = 0.f;
+    float pre[NP][2][2];                    // [pair][row in pair][env in pair]
+    float lsum[2] = {0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < R1; ++i) {
-        const int row = g + G * i;
-        const float2* w = reinterpret_cast<const float2*>(fc1w + row * IN);
-        float2 acc = make_float2(0.f, 0.f);
+    for (int i = 0; i < NP; ++i) {
+        const int rp = g + G * i;
+        float w[2 * IN];
+        const float4* wp = reinterpret_cast<const float4*>(fc1w + rp * 2 * IN);
 #pragma unroll
-        for (int k = 0; k < IN / 2; ++k) acc = ffma2(w[k], ob[k], acc);
-        pre[i] = (acc.x + acc.y) + fc1b[row];
-        lsum += pre[i];
+        for (int v = 0; v < NV; ++v) {
+            const float4 x = wp[v];
+            w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
+        }
+        const float2 bb = *reinterpret_cast<const float2*>(fc1b + 2 * rp);
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < IN / 2; ++k)
+                    acc = ffma2(make_float2(w[r * IN + 2 * k], w[r * IN + 2 * k + 1]), ob[j][k], acc);
+                pre[i][r][j] = (acc.x + acc.y) + (r ? bb.y : bb.x);
+                lsum[j] += pre[i][r][j];
+            }
     }
-    // mean over 512 rows of env e: lanes sharing e, then the 8 warps
-    lsum = group_sum<BT>(lsum);
-    if ((t & 31) < BT) red1[warp * BT + e] = lsum;
+    // mean over the 512 rows of each env: lanes sharing ep, then the warps
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        lsum[j] = group_sum<NEP>(lsum[j]);
+        if (lane < NEP) red1[warp * BT + 2 * ep + j] = lsum[j];
+    }
     __syncthreads();
-    float tot = 0.f;
+    float mean[2], lsq[2] = {0.f, 0.f};
 #pragma unroll
-    for (int w = 0; w < NW; ++w) tot += red1[w * BT + e];
-    const float mean = tot * (1.0f / H1);
-    float lsq = 0.f;
+    for (int j = 0; j < 2; ++j) {
+        float tot = 0.f;
 #pragma unroll
-    for (int i = 0; i < R1; ++i) {
-        pre[i] -= mean;
-        lsq = fmaf(pre[i], pre[i], lsq);
+        for (int w = 0; w < NW; ++w) tot += red1[w * BT + 2 * ep + j];
+        mean[j] = tot * (1.0f / H1);
     }
-    lsq = group_sum<BT>(lsq);
+#pragma unroll
+    for (int i = 0; i < NP; ++i)
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                pre[i][r][j] -= mean[j];
+                lsq[j] = fmaf(pre[i][r][j], pre[i][r][j], lsq[j]);
+            }
     float* red1b = red1 + NW * BT;
-    if ((t & 31) < BT) red1b[warp * BT + e] = lsq;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        lsq[j] = group_sum<NEP>(lsq[j]);
+        if (lane < NEP) red1b[warp * BT + 2 * ep + j] = lsq[j];
+    }
     __syncthreads();
-    tot = 0.f;
+    float rstd[2];
 #pragma unroll
-    for (int w = 0; w < NW; ++w) tot += red1b[w * BT + e];
-    const float var = tot * (1.0f / H1);
-    if (!isfinite(mean) || !isfinite(var)) *flag = 1;
-    const float rstd = 1.0f / sqrtf(var + LN_EPS);
+    for (int j = 0; j < 2; ++j) {
+        float tot = 0.f;
 #pragma unroll
-    for (int i = 0; i < R1; ++i) {
-        const int row = g + G * i;
-        const float v = fmaxf(fmaf(pre[i] * rstd, ln1g[row], ln1b[row]), 0.f);
-        h1p[(row >> 1) * (2 * BT) + 2 * e + (row & 1)] = v;
+        for (int w = 0; w < NW; ++w) tot += red1b[w * BT + 2 * ep + j];
+        const float var = tot * (1.0f / H1);
+        if (!isfinite(mean[j]) || !isfinite(var)) *flag = 1;
+        rstd[j] = 1.0f / sqrtf(var + LN_EPS);
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        const int rp = g + G * i;
+        const float2 gg = *reinterpret_cast<const float2*>(ln1g + 2 * rp);
+        const float2 be = *reinterpret_cast<const float2*>(ln1b + 2 * rp);
+        float4 o;
+        o.x = fmaxf(fmaf(pre[i][0][0] * rstd[0], gg.x, be.x), 0.f);
+        o.y = fmaxf(fmaf(pre[i][1][0] * rstd[0], gg.y, be.y), 0.f);
+        o.z = fmaxf(fmaf(pre[i][0][1] * rstd[1], gg.x, be.x), 0.f);
+        o.w = fmaxf(fmaf(pre[i][1][1] * rstd[1], gg.y, be.y), 0.f);
+        *reinterpret_cast<float4*>(h1p + rp * (2 * BT) + 4 * ep) = o;
     }
 }
 
@@ -159,56 +226,126 @@ __device__ __forceinline__ void layer1(const float* __restrict__ w1a, const floa
 // rows rl + RL*i, i < RPL.  Warp w takes the w-th 4-k step of every 32-k
 // chunk.  Accumulators are float2 (even-k, odd-k partial sums).
 // ---------------------------------------------------------------------------
-template <int BT>
-struct Fc2Map {
-    static constexpr int GE = BT / 4;
-    static constexpr int RL = 32 / GE;
-    static constexpr int RPL = ROWS_Q / RL;
-};
+constexpr int KSPLIT = NW / 2;      // warps sharing a row half split every 32-k chunk 4 ways
 
 template <int BT>
-__device__ __forceinline__ void fc2_step(const float4* __restrict__ wbase, int row_stride_f4, int chunk16,
-                                         const float* __restrict__ h1p, int kbase,
-                                         float2 (&acc)[Fc2Map<BT>::RPL][4]) {
+struct Fc2Map {
+    static constexpr int GE = BT / 4;              // env groups of 4 per warp
+    static constexpr int RL = 32 / GE;             // row lanes
+    static constexpr int RPL = (ROWS_Q / 2) / RL;  // rows per lane inside the warp's 32-row half
+};
+
+// One 32-k chunk for warp (rh = warp & 1, ks = warp >> 1): rows 32*rh + rl + RL*i,
+// k = kbase + {0..7} (two 4-k steps).  `c16` is the 16-byte column of the first step
+// inside the operand's row (resident: 8*ch + 2*ks, staged: 2*ks).
+template <int BT>
+__device__ __forceinline__ void fc2_chunk(const float4* __restrict__ wbase, int row_stride_f4, int c16,
+                                          const float* __restrict__ h1p, int kbase, int row0,
+                                          float2 (&acc)[Fc2Map<BT>::RPL][4]) {
     using M = Fc2Map<BT>;
     const int lane = threadIdx.x & 31;
     const int eg = lane % M::GE, rl = lane / M::GE;
-    // activations: two k-pairs x two env-pairs
-    float4 a[2][2];
+    const int sw = rl & 7;                       // (row & 7) for every row of this lane
+    const float4* wrow0 = wbase + (row0 + rl) * row_stride_f4;
+    const float* hbase = h1p + (kbase >> 1) * (2 * BT) + eg * 8;
 #pragma unroll
-    for (int kp = 0; kp < 2; ++kp)
+    for (int st = 0; st < 2; ++st) {
+        // activations: two k-pairs x two env-pairs
+        float4 a[2][2];
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
-            a[kp][j] = *reinterpret_cast<const float4*>(h1p + ((kbase >> 1) + kp) * (2 * BT) + eg * 8 + j * 4);
+        for (int kp = 0; kp < 2; ++kp)
 #pragma unroll
-    for (int i = 0; i < M::RPL; ++i) {
-        const int row = rl + M::RL * i;
-        const float4 w = wbase[row * row_stride_f4 + (chunk16 ^ (row & 7))];
-        const float2 w0 = make_float2(w.x, w.y), w1 = make_float2(w.z, w.w);
+            for (int j = 0; j < 2; ++j)
+                a[kp][j] = *reinterpret_cast<const float4*>(hbase + (2 * st + kp) * (2 * BT) + j * 4);
+        const int col = (c16 + st) ^ sw;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            acc[i][2 * j] = ffma2(w0, make_float2(a[0][j].x, a[0][j].y), acc[i][2 * j]);
-            acc[i][2 * j] = ffma2(w1, make_float2(a[1][j].x, a[1][j].y), acc[i][2 * j]);
-            acc[i][2 * j + 1] = ffma2(w0, make_float2(a[0][j].z, a[0][j].w), acc[i][2 * j + 1]);
-            acc[i][2 * j + 1] = ffma2(w1, make_float2(a[1][j].z, a[1][j].w), acc[i][2 * j + 1]);
+        for (int i = 0; i < M::RPL; ++i) {
+            const float4 w = wrow0[i * M::RL * row_stride_f4 + col];
+            const float2 w0 = make_float2(w.x, w.y), w1 = make_float2(w.z, w.w);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                acc[i][2 * j] = ffma2(w0, make_float2(a[0][j].x, a[0][j].y), acc[i][2 * j]);
+                acc[i][2 * j] = ffma2(w1, make_float2(a[1][j].x, a[1][j].y), acc[i][2 * j]);
+                acc[i][2 * j + 1] = ffma2(w0, make_float2(a[0][j].z, a[0][j].w), acc[i][2 * j + 1]);
+                acc[i][2 * j + 1] = ffma2(w1, make_float2(a[1][j].z, a[1][j].w), acc[i][2 * j + 1]);
+            }
         }
     }
 }
 
-// issue the cp.async copies of one streamed chunk (64 rows x 32 k) into a stage
-__device__ __forceinline__ void issue_chunk(float4* stage, const float* __restrict__ w2q, int chunk) {
-#pragma unroll
-    for (int i = 0; i < STAGE_F4 / CT; ++i) {
-        const int f = threadIdx.x + i * CT;       // 0..511
-        const int row = f >> 3, j16 = f & 7;
-        cp_async16(stage + row * 8 + (j16 ^ (row & 7)), w2q + (size_t)row * H1 + chunk * KCH + j16 * 4);
+// ---------------------------------------------------------------------------
+// mbarrier + bulk-copy (TMA, non-tensor) plumbing for the streamed operands.
+// A stage is one contiguous, pre-swizzled 8 KB block of the packed opponent
+// matrix, so ONE elected lane moves it with one cp.async.bulk; consumers wait on
+// the stage's "full" mbarrier (completed by the copy's byte count) and release
+// it through the "empty" mbarrier -- no CTA-wide barrier inside the fc2 loop.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// wait for completion #n (n = 0, 1, ...) of the barrier; traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t n) {
+    if (mbar_try_wait(bar, n & 1)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, n & 1)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
     }
 }
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 
-// issue the cp.async copies of a seat's W1 block (contiguous in the flat row)
-__device__ __forceinline__ void issue_w1(float* w1a, const float* __restrict__ wrow, int in_dim) {
-    const int n16 = (H1 * in_dim + 3 * H1) / 4;
-    for (int f = threadIdx.x; f < n16; f += CT) cp_async16(w1a + f * 4, wrow + f * 4);
+// chunk -> stage schedule of one streamed fc2 pass (16 chunks over 6 stages; the tail
+// stays in the dedicated stages so the arena can be refilled with the next W1 block)
+__device__ __forceinline__ int stream_stage(int ch) { return ch < 12 ? ch % 6 : (ch == 15 ? 0 : ch - 12); }
+__device__ __forceinline__ uint32_t stream_local_use(int ch) { return ch < 12 ? ch / 6 : (ch == 15 ? 3 : 2); }
+__device__ __forceinline__ uint32_t stream_uses_per_pass(int st) { return st == 0 ? 4 : (st < 3 ? 3 : 2); }
+
+constexpr uint32_t STAGE_BYTES = STAGE_F4 * 16;
+constexpr int PACKED_F4_PER_ROW = CL * NCHUNK * STAGE_F4;     // float4 per packed fc2 matrix (32768)
+
+// Opponent fc2 matrices repacked into the exact shared-memory stage images:
+// packed[((q*NCHUNK + chunk)*64 + row)*8 + (j16 ^ (row&7))] = W2[64q+row][32*chunk + 4*j16 .. +3]
+__global__ void __launch_bounds__(256) pack_opponent_kernel(const float* __restrict__ rows, int64_t pitch,
+                                                            int in_dim, int K, float4* __restrict__ packed) {
+    const FcOffsets o = fc_offsets(in_dim);
+    const int k = blockIdx.y;
+    const float* w2 = rows + (int64_t)k * pitch + o.fc2w;
+    float4* dst = packed + (int64_t)k * PACKED_F4_PER_ROW;
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < PACKED_F4_PER_ROW; f += gridDim.x * blockDim.x) {
+        const int j16 = f & 7, row = (f >> 3) & 63, chunk = (f >> 9) & (NCHUNK - 1), q = f >> 13;
+        const float4 v = *reinterpret_cast<const float4*>(w2 + (size_t)(q * ROWS_Q + row) * H1 + chunk * KCH + j16 * 4);
+        dst[((q * NCHUNK + chunk) * ROWS_Q + row) * 8 + (j16 ^ (row & 7))] = v;
+    }
+    (void)K;
 }
 
 template <int BT>
@@ -232,16 +369,32 @@ rollout_cluster_kernel(const ClusterParams p) {
     int* act_s = reinterpret_cast<int*>(smem + L::off_act);        // [3][BT]
     float* gap_s = reinterpret_cast<float*>(act_s + 3 * BT);       // [3][BT]
     int* flag = reinterpret_cast<int*>(smem + L::off_flag);
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + L::off_bar);   // [NSTAGE_ALL]
+    uint64_t* bar_empty = bar_full + NSTAGE_ALL;                           // [NSTAGE_ALL]
+    uint64_t* bar_w1 = bar_empty + NSTAGE_ALL;
 
     cg::cluster_group cluster = cg::this_cluster();
     const int q = (int)cluster.block_rank();
     const int cid = blockIdx.x / CL, ncl = gridDim.x / CL;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int e1 = t % BT, g1 = t / BT;
+    const int rh = warp & 1, ks = warp >> 1;      // fc2: row half and k-split index of this warp
     const int ms = p.member_seat;
     const int n_chunks_e = (p.E + BT - 1) / BT;
 
-    if (t == 0) *flag = 0;
+    if (t == 0) {
+        *flag = 0;
+        for (int i = 0; i < NSTAGE_ALL; ++i) {
+            mbar_init(bar_full + i, 1);       // one arrive.expect_tx by the issuing lane
+            mbar_init(bar_empty + i, NW);     // one arrive per consumer warp
+        }
+        mbar_init(bar_w1, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    DBG_LOAD
+    uint32_t sp = 0;       // streamed fc2 passes completed so far (identical in every thread)
+    uint32_t w1n = 0;      // W1 blocks loaded so far
 
     for (int m = cid; m < p.P; m += ncl) {
         const float* mrow = p.members + (int64_t)m * p.member_pitch;
@@ -259,12 +412,16 @@ rollout_cluster_kernel(const ClusterParams p) {
         for (int k = 0; k < p.K; ++k) {
             // per-seat flat rows for this (m, k)
             const float* wrow[3];
+            const float4* wpack[3];     // this CTA's quarter of the packed opponent fc2 matrix
 #pragma unroll
             for (int s = 0; s < 3; ++s) {
-                if (s == ms) wrow[s] = mrow;
-                else {
+                if (s == ms) {
+                    wrow[s] = mrow;
+                    wpack[s] = nullptr;
+                } else {
                     const int oi = (s < ms) ? s : s - 1;
                     wrow[s] = p.opp[oi] + (int64_t)k * p.opp_pitch[oi];
+                    wpack[s] = p.opp_packed[oi] + (int64_t)k * PACKED_F4_PER_ROW + (size_t)q * NCHUNK * STAGE_F4;
                 }
             }
             __syncthreads();      // previous (m,k) done with small[]
@@ -301,25 +458,55 @@ rollout_cluster_kernel(const ClusterParams p) {
 #pragma unroll
                     for (int s = 0; s < 3; ++s) env_observe(st, s, obs + (s * BT + t) * 12);
                 }
-                // seat 0's W1 block
-                issue_w1(w1a, wrow[0], seat_in_dim(0));
-                cp_async_commit();
-                cp_async_wait<0>();       // also covers the member fc2 quarter
+                // seat 0's W1 block (contiguous in the flat row): one bulk copy
+                if (t == 0 && p.n_cycles > 0) {
+                    const uint32_t bytes = (uint32_t)(H1 * seat_in_dim(0) + 3 * H1) * 4;
+                    mbar_arrive_expect_tx(bar_w1, bytes);
+                    bulk_g2s(w1a, wrow[0], bytes, bar_w1);
+                }
+                cp_async_wait<0>();       // the member fc2 quarter
                 __syncthreads();
 
+                PROF_DECL
                 for (int c = 0; c < p.n_cycles; ++c) {
                     float pre2[3][RP];
+                    PROF(0);
                     // =========== three independent forwards ====================
                     // (fully unrolled: pre2[s] must stay in registers)
 #pragma unroll
                     for (int s = 0; s < 3; ++s) {
+                        // ---- streamed seats: chunks 0..2 go to the dedicated stages and are
+                        //      issued now, so they land while layer 1 runs
+                        const float4* src = wpack[s];
+                        auto issue = [&](int ch) {
+                            const int st = stream_stage(ch);
+                            const uint32_t use = sp * stream_uses_per_pass(st) + stream_local_use(ch);
+                            if (use > 0) mbar_wait(bar_empty + st, use - 1);
+                            float4* dst = st < NSTAGE ? stage + st * STAGE_F4
+                                                      : reinterpret_cast<float4*>(w1a) + (st - NSTAGE) * STAGE_F4;
+                            mbar_arrive_expect_tx(bar_full + st, STAGE_BYTES);
+                            bulk_g2s(dst, src + (size_t)ch * STAGE_F4, STAGE_BYTES, bar_full + st);
+                        };
+                        auto issue_w1 = [&](int seat) {
+                            const uint32_t bytes = (uint32_t)(H1 * seat_in_dim(seat) + 3 * H1) * 4;
+                            mbar_arrive_expect_tx(bar_w1, bytes);
+                            bulk_g2s(w1a, wrow[seat], bytes, bar_w1);
+                        };
+                        const int sn = (s + 1) % 3;
+                        const bool more = !(s == 2 && c == p.n_cycles - 1);   // another forward follows
+                        if (s != ms && t == 0 && !DBG_FLAG(2)) {
+                            issue(0);
+                            issue(1);
+                            issue(2);
+                        }
                         // ---- layer 1 (reads w1a, obs; writes h1p) --------------
+                        mbar_wait(bar_w1, w1n);
+                        ++w1n;
+                        PROF(1);
                         if (s == 0) layer1<BT, IN_ADV>(w1a, obs + s * BT * 12, u, red1, flag);
                         else layer1<BT, IN_GOOD>(w1a, obs + s * BT * 12, u, red1, flag);
-                        __syncthreads();          // h1p complete; w1a free
-                        // ---- prefetch next seat's W1 block ---------------------
-                        const int sn = (s + 1) % 3;
-                        issue_w1(w1a, wrow[sn], seat_in_dim(sn));
+                        __syncthreads();          // h1p complete; the W1 arena is free
+                        PROF(2);
                         // ---- fc2 quarter --------------------------------------
                         float2 acc[M::RPL][4];
 #pragma unroll
@@ -327,43 +514,67 @@ rollout_cluster_kernel(const ClusterParams p) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
                         if (s == ms) {
-                            cp_async_commit();
+                            // resident operand; the arena is idle, prefetch the next seat's W1 block
+                            if (t == 0 && more) issue_w1(sn);
 #pragma unroll 2
                             for (int ch = 0; ch < NCHUNK; ++ch)
-                                fc2_step<BT>(w2m, 128, ch * 8 + warp, u, ch * KCH + warp * 4, acc);
-                            cp_async_wait<0>();
+                                fc2_chunk<BT>(w2m, 128, ch * 8 + 2 * ks, u, ch * KCH + 8 * ks, 32 * rh, acc);
+                            PROF(3);
                         } else {
-                            const FcOffsets o = fc_offsets(seat_in_dim(s));
-                            const float* w2q = wrow[s] + o.fc2w + (size_t)q * ROWS_Q * H1;
-                            issue_chunk(stage, w2q, 0);
-                            cp_async_commit();                 // group: W1(next) + chunk 0
-                            issue_chunk(stage + STAGE_F4, w2q, 1);
-                            cp_async_commit();                 // group: chunk 1
+                            // Streamed operand: 6 pre-swizzled 8 KB stages (3 dedicated + 3 in the idle
+                            // W1 arena), 4 in flight.  At the top of iteration ch, lane 0 of warp
+                            // (ch % NW) issues the chunk that reuses the stage released by chunk ch-2
+                            // (its "empty" mbarrier has normally completed an iteration ago, so the
+                            // issuing warp does not stall on its peers); no warp ever waits on a
+                            // CTA-wide barrier inside this loop.  The arena stages are last used by
+                            // chunks 9..11, so the next seat's W1 block is issued at iteration 14 and
+                            // lands under chunks 14..15 and the reduction that follows.
+                            if (t == 0 && !DBG_FLAG(2)) {
+                                issue(3);
+                                issue(4);
+                                issue(5);
+                            }
 #pragma unroll 1
                             for (int ch = 0; ch < NCHUNK; ++ch) {
-                                cp_async_wait<NSTAGE - 2>();   // chunk ch has landed (this thread)
-                                __syncthreads();               // ... for all threads; chunk ch-1 consumed
-                                if (ch + 2 < NCHUNK)
-                                    issue_chunk(stage + ((ch + 2) % NSTAGE) * STAGE_F4, w2q, ch + 2);
-                                cp_async_commit();
-                                fc2_step<BT>(stage + (ch % NSTAGE) * STAGE_F4, 8, warp, u,
-                                             ch * KCH + warp * 4, acc);
+                                if (warp == (ch % NW)) {
+                                    if (lane == 0) {
+                                        const int nx = (ch >= 2 && ch <= 10) ? ch + 4 : (ch == 14 ? 15 : -1);
+                                        if (nx >= 0 && !DBG_FLAG(2)) issue(nx);
+                                        if (ch == 14 && more) {
+                                            // arena stages 3..5: second (last) use of this pass
+                                            if (!DBG_FLAG(2))
+                                                for (int st = NSTAGE; st < NSTAGE_ALL; ++st)
+                                                    mbar_wait(bar_empty + st, sp * 2 + 1);
+                                            issue_w1(sn);
+                                        }
+                                    }
+                                    __syncwarp();      // keep the issuing warp converged
+                                }
+                                const int st = stream_stage(ch);
+                                const uint32_t use = sp * stream_uses_per_pass(st) + stream_local_use(ch);
+                                if (!DBG_FLAG(3)) mbar_wait(bar_full + st, use);
+                                const float4* wst = st < NSTAGE ? stage + st * STAGE_F4
+                                                                : reinterpret_cast<const float4*>(w1a) + (st - NSTAGE) * STAGE_F4;
+                                fc2_chunk<BT>(wst, 8, 2 * ks, u, ch * KCH + 8 * ks, 32 * rh, acc);
+                                __syncwarp();
+                                if (lane == 0 && !DBG_FLAG(2)) mbar_arrive(bar_empty + st);
                             }
-                            cp_async_wait<0>();
+                            ++sp;
+                            PROF(4);
                         }
-                        __syncthreads();          // all warps done reading h1p; W1(next) landed
+                        __syncthreads();          // all warps done reading h1p
                         // ---- k-split partials -> part[warp][row][e] (aliases h1p)
                         {
                             const int eg = lane % M::GE, rl = lane / M::GE;
 #pragma unroll
                             for (int i = 0; i < M::RPL; ++i) {
-                                const int row = rl + M::RL * i;
+                                const int row = 32 * rh + rl + M::RL * i;
                                 float4 v;
                                 v.x = acc[i][0].x + acc[i][0].y;
                                 v.y = acc[i][1].x + acc[i][1].y;
                                 v.z = acc[i][2].x + acc[i][2].y;
                                 v.w = acc[i][3].x + acc[i][3].y;
-                                *reinterpret_cast<float4*>(u + (warp * ROWS_Q + row) * BT + eg * 4) = v;
+                                *reinterpret_cast<float4*>(u + (ks * ROWS_Q + row) * BT + eg * 4) = v;
                             }
                         }
                         __syncthreads();
@@ -374,11 +585,12 @@ rollout_cluster_kernel(const ClusterParams p) {
                                 const int row = g1 + G * j;
                                 float sacc = u[row * BT + e1];
 #pragma unroll
-                                for (int w = 1; w < NW; ++w) sacc += u[(w * ROWS_Q + row) * BT + e1];
+                                for (int w = 1; w < KSPLIT; ++w) sacc += u[(w * ROWS_Q + row) * BT + e1];
                                 pre2[s][j] = sacc + b2[row];
                             }
                         }
                         __syncthreads();          // part consumed; u free for the next seat
+                        PROF(5);
                     }
                     // =========== LayerNorm-2 statistics across the cluster =====
                     // local (64-row) mean and M2 per seat/env, then Chan combine.
@@ -425,7 +637,9 @@ rollout_cluster_kernel(const ClusterParams p) {
                             dst[(s * CL + q) * BT + e] = v;
                         }
                     }
+                    PROF(6);
                     cluster.sync();                        // barrier 1
+                    PROF(7);
                     // =========== normalise, partial logits ======================
                     float* redC = u + 6 * NW * BT;         // [3][NW][5][BT]
 #pragma unroll
@@ -474,7 +688,9 @@ rollout_cluster_kernel(const ClusterParams p) {
                             dst[((s * CL + q) * NACT + a) * BT + e] = tot;
                         }
                     }
+                    PROF(8);
                     cluster.sync();                        // barrier 2
+                    PROF(9);
                     // =========== logits, argmax, physics ========================
                     if (t < 3 * BT) {
                         const int s = t / BT, e = t % BT;
@@ -571,11 +787,46 @@ int rollout_cluster_max_clusters(int device) {
     return n;
 }
 
-int launch_rollout_cluster(cev_handle* h, const ClusterParams& p, cudaStream_t stream) {
-    if (p.P <= 0 || p.K <= 0 || p.E <= 0) return CEV_OK;
+int launch_rollout_cluster(cev_handle* h, const ClusterParams& p_in, cudaStream_t stream) {
+    if (p_in.P <= 0 || p_in.K <= 0 || p_in.E <= 0) return CEV_OK;
+    ClusterParams p = p_in;
+    // repack the (few) opponent fc2 matrices into stage images: 512 KB per row and seat
+    const size_t per_seat = (size_t)p.K * PACKED_F4_PER_ROW * sizeof(float4);
+    if (h->opp_workspace_bytes < 2 * per_seat) {
+        if (h->opp_workspace) CEV_CUDA(cudaFree(h->opp_workspace));
+        h->opp_workspace = nullptr;
+        h->opp_workspace_bytes = 0;
+        CEV_CUDA(cudaMalloc(&h->opp_workspace, 2 * per_seat));
+        h->opp_workspace_bytes = 2 * per_seat;
+    }
+    for (int oi = 0; oi < 2; ++oi) {
+        const int seat = (oi < p.member_seat) ? oi : oi + 1;
+        float4* dst = reinterpret_cast<float4*>(static_cast<char*>(h->opp_workspace) + oi * per_seat);
+        pack_opponent_kernel<<<dim3(32, p.K), 256, 0, stream>>>(p.opp[oi], p.opp_pitch[oi], seat_in_dim(seat), p.K,
+                                                               dst);
+        p.opp_packed[oi] = dst;
+    }
+    CEV_CUDA(cudaGetLastError());
     if (p.E > 8) return launch_bt<16>(h, p, stream);
     if (p.E > 4) return launch_bt<8>(h, p, stream);
     return launch_bt<4>(h, p, stream);
 }
 
 }  // namespace cev
+
+#ifdef CEV_PROFILE
+// development-only: read (and optionally reset) the phase timers
+extern "C" int cev_debug_profile(double* out, int n, int reset) {
+    unsigned long long h[16];
+    if (cudaMemcpyFromSymbol(h, cev_prof_acc, sizeof(h)) != cudaSuccess) return -1;
+    for (int i = 0; i < n && i < 16; ++i) out[i] = (double)h[i];
+    if (reset) {
+        unsigned long long z[16] = {};
+        cudaMemcpyToSymbol(cev_prof_acc, z, sizeof(z));
+    }
+    return 0;
+}
+extern "C" int cev_debug_set_flags(int flags) {
+    return cudaMemcpyToSymbol(cev_debug_flags, &flags, sizeof(int)) == cudaSuccess ? 0 : -1;
+}
+#endif

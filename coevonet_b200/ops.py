@@ -16,7 +16,7 @@ from ._lib import RolloutCfg, check, handle, load
 MAX_CYCLES = 25
 
 #: kernels launched per C-ABI call (bench.py reports the total as ``gpu_launches``)
-_KERNELS_PER_CALL = {"cev_es_update_f32": 2, "cev_fp32_peak": 4}
+_KERNELS_PER_CALL = {"cev_es_update_f32": 2, "cev_fp32_peak": 4, "cev_mpe_rollout_f32": 3}
 launch_count = 0
 
 
