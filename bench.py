@@ -189,6 +189,10 @@ def run_gpu_arm(ns):
     from coevonet_b200 import engine, layout, ops
     from coevonet_b200.MPE.fcnetwork import FCNetwork
 
+    # stdout carries exactly one JSON line: keep NCCL's banner ("NCCL version ...") off it
+    os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

@@ -1,0 +1,62 @@
+"""K2 parity: grouped per-member DeepQN forward (through the C ABI) vs the
+reference's own DeepQN.forward outputs (tests/golden/deepqn.npz) and the oracle.
+Tolerance: fp32 arithmetic with a different summation order -> 2e-5 absolute on
+logits of magnitude ~0.2."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import deepqn as odqn
+from oracle import weights
+
+pytestmark = pytest.mark.gpu
+
+
+def _pad(rows, c_in, n_act):
+    from coevonet_b200 import layout
+    out = np.zeros((rows.shape[0], layout.dqn_pitch(c_in, n_act)), dtype=np.float32)
+    out[:, :rows.shape[1]] = rows
+    return torch.from_numpy(out).cuda()
+
+
+@pytest.mark.parametrize("c_in,n_act", [(4, 6), (4, 18), (6, 18)])
+def test_deepqn_forward_matches_reference_golden(golden, c_in, n_act):
+    from coevonet_b200 import ops
+    g = golden("deepqn")
+    rows = weights.make_dqn_rows(2, c_in, n_act, 600 + c_in + n_act, bn_jitter=float(g["bn_jitter"]))
+    rng = np.random.Generator(np.random.PCG64(int(g["frame_seed"])))
+    frames = rng.integers(0, 256, (2, 2, c_in, 84, 84), dtype=np.uint8)
+    logits, actions = ops.deepqn_forward(_pad(rows, c_in, n_act), torch.from_numpy(frames).cuda(), c_in, n_act)
+    want = g[f"c{c_in}a{n_act}.logits"]
+    np.testing.assert_allclose(logits.cpu().numpy(), want, rtol=0, atol=2e-5)
+    assert np.array_equal(actions.cpu().numpy(), np.argmax(want, axis=-1))
+
+
+def test_deepqn_many_frames_and_members_vs_oracle():
+    from coevonet_b200 import ops
+    c_in, n_act, P, B = 4, 6, 3, 13                      # B > frames-per-fc-pass exercises chunking
+    rows = weights.make_dqn_rows(P, c_in, n_act, 91, bn_jitter=0.1)
+    frames = ops.random_frames(5, (P, B, c_in, 84, 84), "cuda")
+    logits, actions = ops.deepqn_forward(_pad(rows, c_in, n_act), frames, c_in, n_act)
+    want, want_act = odqn.dqn_forward_batch(rows, frames.cpu().numpy(), c_in, n_act)
+    np.testing.assert_allclose(logits.cpu().numpy(), want, rtol=0, atol=3e-5)
+    srt = np.sort(want, axis=-1)
+    safe = (srt[..., -1] - srt[..., -2]) > 1e-4
+    assert np.array_equal(actions.cpu().numpy()[safe], want_act[safe])
+    # per-frame BatchNorm: a frame's logits do not depend on its batch neighbours
+    solo, _ = ops.deepqn_forward(_pad(rows, c_in, n_act)[1:2].contiguous(), frames[1:2, 4:5].contiguous(), c_in, n_act)
+    assert torch.equal(solo[0, 0], logits[1, 4])
+
+
+def test_deepqn_module_dropin():
+    from coevonet_b200.Atari.deepqn import DeepQN
+    torch.manual_seed(3)
+    net = DeepQN(4, 6, "float32")
+    x = torch.randint(0, 256, (2, 4, 84, 84)).float()
+    got = net.forward(x)
+    sd = {k: v.numpy() for k, v in net.state_dict().items()}
+    from oracle import layout as olayout
+    row = olayout.pack_dqn_state_dict(sd, 4, 6)
+    want, _ = odqn.dqn_forward_batch(row[None], x.numpy().astype(np.uint8)[None], 4, 6)
+    np.testing.assert_allclose(got.numpy(), want[0], rtol=0, atol=3e-5)
+    assert net.determine_action(x[:1]) == int(np.argmax(want[0, 0]))
