@@ -62,11 +62,11 @@ constexpr int CL = 4;                       // CTAs per cluster
 constexpr int CT = 256;                     // threads per CTA
 constexpr int NW = CT / 32;                 // warps per CTA
 constexpr int ROWS_Q = H2 / CL;             // fc2 rows per CTA (64)
-constexpr int KCH = 32;                     // k per streamed chunk
-constexpr int NCHUNK = H1 / KCH;            // 16
-constexpr int NSTAGE = 3;                   // dedicated 8 KB stages (region `stage`)
-constexpr int NSTAGE_ALL = 6;               // + 3 stages borrowed from the W1 arena during a streamed pass
-constexpr int STAGE_F4 = ROWS_Q * KCH / 4;  // float4 per stage (512)
+constexpr int KCH = 16;                     // k per chunk: one warp owns a whole chunk (4 steps of 4 k)
+constexpr int NCHUNK = H1 / KCH;            // 32 chunks per fc2 pass, warp w owns chunks w, w+8, w+16, w+24
+constexpr int NSLOT_D = 6;                  // dedicated 4 KB slots (region `stage`)
+constexpr int NSLOT = 12;                   // + 6 slots borrowed from the W1 arena during a streamed pass
+constexpr int STAGE_F4 = ROWS_Q * KCH / 4;  // float4 per slot (256 = 4 KB)
 constexpr int W1A_FLOATS = H1 * IN_GOOD + 3 * H1;   // fc1.W | fc1.b | ln1.g | ln1.b
 constexpr int SMALL_FLOATS = 512;           // b2[64] g2[64] be2[64] w3[5][64]
 
@@ -75,7 +75,7 @@ struct SmemLayout {
     static constexpr size_t off_w2m = 0;
     static constexpr size_t off_w1a = off_w2m + (size_t)ROWS_Q * H1 * 4;
     static constexpr size_t off_stage = off_w1a + (size_t)W1A_FLOATS * 4;
-    static constexpr size_t off_u = off_stage + (size_t)NSTAGE * STAGE_F4 * 16;
+    static constexpr size_t off_u = off_stage + (size_t)NSLOT_D * STAGE_F4 * 16;
     static constexpr size_t off_small = off_u + (size_t)H1 * BT * 4;
     static constexpr size_t off_obs = off_small + (size_t)(3 * SMALL_FLOATS + 24) * 4;
     static constexpr size_t off_red1 = off_obs + (size_t)3 * BT * 12 * 4;
@@ -83,7 +83,7 @@ struct SmemLayout {
     static constexpr size_t off_plog = off_lnx + (size_t)3 * CL * BT * 8;
     static constexpr size_t off_act = off_plog + (size_t)3 * CL * NACT * BT * 4;
     static constexpr size_t off_flag = off_act + (size_t)3 * BT * 8;
-    static constexpr size_t off_bar = off_flag + 16;             // full[6], empty[6], w1_full
+    static constexpr size_t off_bar = off_flag + 16;             // full[NSLOT], w1_full
     static constexpr size_t total = off_bar + 128;
 };
 
@@ -226,30 +226,32 @@ __device__ __forceinline__ void layer1(const float* __restrict__ w1a, const floa
 // rows rl + RL*i, i < RPL.  Warp w takes the w-th 4-k step of every 32-k
 // chunk.  Accumulators are float2 (even-k, odd-k partial sums).
 // ---------------------------------------------------------------------------
-constexpr int KSPLIT = NW / 2;      // warps sharing a row half split every 32-k chunk 4 ways
-
 template <int BT>
 struct Fc2Map {
     static constexpr int GE = BT / 4;              // env groups of 4 per warp
     static constexpr int RL = 32 / GE;             // row lanes
-    static constexpr int RPL = (ROWS_Q / 2) / RL;  // rows per lane inside the warp's 32-row half
+    static constexpr int RPL = ROWS_Q / RL;        // rows per lane (all 64 rows of the CTA's quarter)
 };
 
-// One 32-k chunk for warp (rh = warp & 1, ks = warp >> 1): rows 32*rh + rl + RL*i,
-// k = kbase + {0..7} (two 4-k steps).  `c16` is the 16-byte column of the first step
-// inside the operand's row (resident: 8*ch + 2*ks, staged: 2*ks).
-template <int BT>
-__device__ __forceinline__ void fc2_chunk(const float4* __restrict__ wbase, int row_stride_f4, int c16,
-                                          const float* __restrict__ h1p, int kbase, int row0,
+// One 16-k chunk (4 steps of 4 k) of the fc2 quarter for ONE warp: rows rl + RL*i,
+// k = kbase .. kbase+15, all BT envs.  Accumulators are float2 (even-k, odd-k sums).
+//  STAGED = false: resident operand, row stride 128 float4, 16-byte column c16_0 + step,
+//                  swizzled by (row & 7);
+//  STAGED = true : 4 KB slot image, row stride 4 float4, column = step, swizzled by
+//                  ((row >> 1) & 3) (8 consecutive rows -> 8 distinct 16-byte bank groups).
+template <int BT, bool STAGED>
+__device__ __forceinline__ void fc2_chunk(const float4* __restrict__ wbase, int c16_0,
+                                          const float* __restrict__ h1p, int kbase,
                                           float2 (&acc)[Fc2Map<BT>::RPL][4]) {
     using M = Fc2Map<BT>;
+    constexpr int RS = STAGED ? 4 : 128;         // row stride in float4
     const int lane = threadIdx.x & 31;
     const int eg = lane % M::GE, rl = lane / M::GE;
-    const int sw = rl & 7;                       // (row & 7) for every row of this lane
-    const float4* wrow0 = wbase + (row0 + rl) * row_stride_f4;
+    const int sw = STAGED ? ((rl >> 1) & 3) : (rl & 7);
+    const float4* wrow0 = wbase + rl * RS;
     const float* hbase = h1p + (kbase >> 1) * (2 * BT) + eg * 8;
 #pragma unroll
-    for (int st = 0; st < 2; ++st) {
+    for (int st = 0; st < KCH / 4; ++st) {
         // activations: two k-pairs x two env-pairs
         float4 a[2][2];
 #pragma unroll
@@ -257,10 +259,10 @@ __device__ __forceinline__ void fc2_chunk(const float4* __restrict__ wbase, int 
 #pragma unroll
             for (int j = 0; j < 2; ++j)
                 a[kp][j] = *reinterpret_cast<const float4*>(hbase + (2 * st + kp) * (2 * BT) + j * 4);
-        const int col = (c16 + st) ^ sw;
+        const int col = (c16_0 + st) ^ sw;
 #pragma unroll
         for (int i = 0; i < M::RPL; ++i) {
-            const float4 w = wrow0[i * M::RL * row_stride_f4 + col];
+            const float4 w = wrow0[i * M::RL * RS + col];
             const float2 w0 = make_float2(w.x, w.y), w1 = make_float2(w.z, w.w);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -323,17 +325,11 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                  : "memory");
 }
 
-// chunk -> stage schedule of one streamed fc2 pass (16 chunks over 6 stages; the tail
-// stays in the dedicated stages so the arena can be refilled with the next W1 block)
-__device__ __forceinline__ int stream_stage(int ch) { return ch < 12 ? ch % 6 : (ch == 15 ? 0 : ch - 12); }
-__device__ __forceinline__ uint32_t stream_local_use(int ch) { return ch < 12 ? ch / 6 : (ch == 15 ? 3 : 2); }
-__device__ __forceinline__ uint32_t stream_uses_per_pass(int st) { return st == 0 ? 4 : (st < 3 ? 3 : 2); }
-
 constexpr uint32_t STAGE_BYTES = STAGE_F4 * 16;
 constexpr int PACKED_F4_PER_ROW = CL * NCHUNK * STAGE_F4;     // float4 per packed fc2 matrix (32768)
 
 // Opponent fc2 matrices repacked into the exact shared-memory stage images:
-// packed[((q*NCHUNK + chunk)*64 + row)*8 + (j16 ^ (row&7))] = W2[64q+row][32*chunk + 4*j16 .. +3]
+// packed[((q*NCHUNK + chunk)*64 + row)*4 + (j16 ^ ((row>>1)&3))] = W2[64q+row][16*chunk + 4*j16 .. +3]
 __global__ void __launch_bounds__(256) pack_opponent_kernel(const float* __restrict__ rows, int64_t pitch,
                                                             int in_dim, int K, float4* __restrict__ packed) {
     const FcOffsets o = fc_offsets(in_dim);
@@ -341,9 +337,9 @@ __global__ void __launch_bounds__(256) pack_opponent_kernel(const float* __restr
     const float* w2 = rows + (int64_t)k * pitch + o.fc2w;
     float4* dst = packed + (int64_t)k * PACKED_F4_PER_ROW;
     for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < PACKED_F4_PER_ROW; f += gridDim.x * blockDim.x) {
-        const int j16 = f & 7, row = (f >> 3) & 63, chunk = (f >> 9) & (NCHUNK - 1), q = f >> 13;
+        const int j16 = f & 3, row = (f >> 2) & 63, chunk = (f >> 8) & (NCHUNK - 1), q = f >> 13;
         const float4 v = *reinterpret_cast<const float4*>(w2 + (size_t)(q * ROWS_Q + row) * H1 + chunk * KCH + j16 * 4);
-        dst[((q * NCHUNK + chunk) * ROWS_Q + row) * 8 + (j16 ^ (row & 7))] = v;
+        dst[((q * NCHUNK + chunk) * ROWS_Q + row) * 4 + (j16 ^ ((row >> 1) & 3))] = v;
     }
     (void)K;
 }
@@ -369,25 +365,20 @@ rollout_cluster_kernel(const ClusterParams p) {
     int* act_s = reinterpret_cast<int*>(smem + L::off_act);        // [3][BT]
     float* gap_s = reinterpret_cast<float*>(act_s + 3 * BT);       // [3][BT]
     int* flag = reinterpret_cast<int*>(smem + L::off_flag);
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + L::off_bar);   // [NSTAGE_ALL]
-    uint64_t* bar_empty = bar_full + NSTAGE_ALL;                           // [NSTAGE_ALL]
-    uint64_t* bar_w1 = bar_empty + NSTAGE_ALL;
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + L::off_bar);   // [NSLOT]
+    uint64_t* bar_w1 = bar_full + NSLOT;
 
     cg::cluster_group cluster = cg::this_cluster();
     const int q = (int)cluster.block_rank();
     const int cid = blockIdx.x / CL, ncl = gridDim.x / CL;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int e1 = t % BT, g1 = t / BT;
-    const int rh = warp & 1, ks = warp >> 1;      // fc2: row half and k-split index of this warp
     const int ms = p.member_seat;
     const int n_chunks_e = (p.E + BT - 1) / BT;
 
     if (t == 0) {
         *flag = 0;
-        for (int i = 0; i < NSTAGE_ALL; ++i) {
-            mbar_init(bar_full + i, 1);       // one arrive.expect_tx by the issuing lane
-            mbar_init(bar_empty + i, NW);     // one arrive per consumer warp
-        }
+        for (int i = 0; i < NSLOT; ++i) mbar_init(bar_full + i, 1);   // one arrive.expect_tx per fill
         mbar_init(bar_w1, 1);
         mbar_fence_init();
     }
@@ -475,17 +466,15 @@ rollout_cluster_kernel(const ClusterParams p) {
                     // (fully unrolled: pre2[s] must stay in registers)
 #pragma unroll
                     for (int s = 0; s < 3; ++s) {
-                        // ---- streamed seats: chunks 0..2 go to the dedicated stages and are
-                        //      issued now, so they land while layer 1 runs
+                        // ---- streamed seats: a slot is one 4 KB chunk image; chunk ch lives in slot
+                        //      ch % 12 (6 dedicated + 6 borrowed from the W1 arena once layer 1 is done)
                         const float4* src = wpack[s];
                         auto issue = [&](int ch) {
-                            const int st = stream_stage(ch);
-                            const uint32_t use = sp * stream_uses_per_pass(st) + stream_local_use(ch);
-                            if (use > 0) mbar_wait(bar_empty + st, use - 1);
-                            float4* dst = st < NSTAGE ? stage + st * STAGE_F4
-                                                      : reinterpret_cast<float4*>(w1a) + (st - NSTAGE) * STAGE_F4;
-                            mbar_arrive_expect_tx(bar_full + st, STAGE_BYTES);
-                            bulk_g2s(dst, src + (size_t)ch * STAGE_F4, STAGE_BYTES, bar_full + st);
+                            const int sl = ch % NSLOT;
+                            float4* dst = sl < NSLOT_D ? stage + sl * STAGE_F4
+                                                       : reinterpret_cast<float4*>(w1a) + (sl - NSLOT_D) * STAGE_F4;
+                            mbar_arrive_expect_tx(bar_full + sl, STAGE_BYTES);
+                            bulk_g2s(dst, src + (size_t)ch * STAGE_F4, STAGE_BYTES, bar_full + sl);
                         };
                         auto issue_w1 = [&](int seat) {
                             const uint32_t bytes = (uint32_t)(H1 * seat_in_dim(seat) + 3 * H1) * 4;
@@ -495,9 +484,9 @@ rollout_cluster_kernel(const ClusterParams p) {
                         const int sn = (s + 1) % 3;
                         const bool more = !(s == 2 && c == p.n_cycles - 1);   // another forward follows
                         if (s != ms && t == 0 && !DBG_FLAG(2)) {
-                            issue(0);
-                            issue(1);
-                            issue(2);
+                            // chunks 0..5 land in the dedicated slots while layer 1 runs
+#pragma unroll
+                            for (int ch = 0; ch < NSLOT_D; ++ch) issue(ch);
                         }
                         // ---- layer 1 (reads w1a, obs; writes h1p) --------------
                         mbar_wait(bar_w1, w1n);
@@ -507,7 +496,7 @@ rollout_cluster_kernel(const ClusterParams p) {
                         else layer1<BT, IN_GOOD>(w1a, obs + s * BT * 12, u, red1, flag);
                         __syncthreads();          // h1p complete; the W1 arena is free
                         PROF(2);
-                        // ---- fc2 quarter --------------------------------------
+                        // ---- fc2 quarter: warp w owns the 16-k chunks w, w+8, w+16, w+24 ------
                         float2 acc[M::RPL][4];
 #pragma unroll
                         for (int i = 0; i < M::RPL; ++i)
@@ -516,65 +505,51 @@ rollout_cluster_kernel(const ClusterParams p) {
                         if (s == ms) {
                             // resident operand; the arena is idle, prefetch the next seat's W1 block
                             if (t == 0 && more) issue_w1(sn);
-#pragma unroll 2
-                            for (int ch = 0; ch < NCHUNK; ++ch)
-                                fc2_chunk<BT>(w2m, 128, ch * 8 + 2 * ks, u, ch * KCH + 8 * ks, 32 * rh, acc);
+#pragma unroll
+                            for (int r = 0; r < NCHUNK / NW; ++r) {
+                                const int ch = warp + NW * r;
+                                fc2_chunk<BT, false>(w2m, ch * (KCH / 4), u, ch * KCH, acc);
+                            }
                             PROF(3);
                         } else {
-                            // Streamed operand: 6 pre-swizzled 8 KB stages (3 dedicated + 3 in the idle
-                            // W1 arena), 4 in flight.  At the top of iteration ch, lane 0 of warp
-                            // (ch % NW) issues the chunk that reuses the stage released by chunk ch-2
-                            // (its "empty" mbarrier has normally completed an iteration ago, so the
-                            // issuing warp does not stall on its peers); no warp ever waits on a
-                            // CTA-wide barrier inside this loop.  The arena stages are last used by
-                            // chunks 9..11, so the next seat's W1 block is issued at iteration 14 and
-                            // lands under chunks 14..15 and the reduction that follows.
+                            // Streamed operand through TMA bulk copies.  A chunk has exactly ONE
+                            // consumer warp, so there are no "empty" barriers and no warp ever waits
+                            // for a peer: after its 256 FFMA2 on chunk ch, the owning warp's lane 0
+                            // refills the slot it just drained with chunk ch+12 (owned by another
+                            // warp, which waits on the slot's "full" mbarrier).
                             if (t == 0 && !DBG_FLAG(2)) {
-                                issue(3);
-                                issue(4);
-                                issue(5);
+#pragma unroll
+                                for (int ch = NSLOT_D; ch < NSLOT; ++ch) issue(ch);
                             }
 #pragma unroll 1
-                            for (int ch = 0; ch < NCHUNK; ++ch) {
-                                if (warp == (ch % NW)) {
-                                    if (lane == 0) {
-                                        const int nx = (ch >= 2 && ch <= 10) ? ch + 4 : (ch == 14 ? 15 : -1);
-                                        if (nx >= 0 && !DBG_FLAG(2)) issue(nx);
-                                        if (ch == 14 && more) {
-                                            // arena stages 3..5: second (last) use of this pass
-                                            if (!DBG_FLAG(2))
-                                                for (int st = NSTAGE; st < NSTAGE_ALL; ++st)
-                                                    mbar_wait(bar_empty + st, sp * 2 + 1);
-                                            issue_w1(sn);
-                                        }
-                                    }
-                                    __syncwarp();      // keep the issuing warp converged
-                                }
-                                const int st = stream_stage(ch);
-                                const uint32_t use = sp * stream_uses_per_pass(st) + stream_local_use(ch);
-                                if (!DBG_FLAG(3)) mbar_wait(bar_full + st, use);
-                                const float4* wst = st < NSTAGE ? stage + st * STAGE_F4
-                                                                : reinterpret_cast<const float4*>(w1a) + (st - NSTAGE) * STAGE_F4;
-                                fc2_chunk<BT>(wst, 8, 2 * ks, u, ch * KCH + 8 * ks, 32 * rh, acc);
+                            for (int r = 0; r < NCHUNK / NW; ++r) {
+                                const int ch = warp + NW * r;
+                                const int sl = ch % NSLOT;
+                                const uint32_t use = sp * (sl < 8 ? 3u : 2u) + (uint32_t)(ch / NSLOT);
+                                if (!DBG_FLAG(3)) mbar_wait(bar_full + sl, use);
+                                const float4* wst = sl < NSLOT_D ? stage + sl * STAGE_F4
+                                                                 : reinterpret_cast<const float4*>(w1a) + (sl - NSLOT_D) * STAGE_F4;
+                                fc2_chunk<BT, true>(wst, 0, u, ch * KCH, acc);
                                 __syncwarp();
-                                if (lane == 0 && !DBG_FLAG(2)) mbar_arrive(bar_empty + st);
+                                if (lane == 0 && ch + NSLOT < NCHUNK && !DBG_FLAG(2)) issue(ch + NSLOT);
                             }
                             ++sp;
                             PROF(4);
                         }
-                        __syncthreads();          // all warps done reading h1p
+                        __syncthreads();          // all warps done reading h1p and the arena slots
+                        if (s != ms && t == 0 && more) issue_w1(sn);
                         // ---- k-split partials -> part[warp][row][e] (aliases h1p)
                         {
                             const int eg = lane % M::GE, rl = lane / M::GE;
 #pragma unroll
                             for (int i = 0; i < M::RPL; ++i) {
-                                const int row = 32 * rh + rl + M::RL * i;
+                                const int row = rl + M::RL * i;
                                 float4 v;
                                 v.x = acc[i][0].x + acc[i][0].y;
                                 v.y = acc[i][1].x + acc[i][1].y;
                                 v.z = acc[i][2].x + acc[i][2].y;
                                 v.w = acc[i][3].x + acc[i][3].y;
-                                *reinterpret_cast<float4*>(u + (ks * ROWS_Q + row) * BT + eg * 4) = v;
+                                *reinterpret_cast<float4*>(u + (warp * ROWS_Q + row) * BT + eg * 4) = v;
                             }
                         }
                         __syncthreads();
@@ -585,7 +560,7 @@ rollout_cluster_kernel(const ClusterParams p) {
                                 const int row = g1 + G * j;
                                 float sacc = u[row * BT + e1];
 #pragma unroll
-                                for (int w = 1; w < KSPLIT; ++w) sacc += u[(w * ROWS_Q + row) * BT + e1];
+                                for (int w = 1; w < NW; ++w) sacc += u[(w * ROWS_Q + row) * BT + e1];
                                 pre2[s][j] = sacc + b2[row];
                             }
                         }
