@@ -273,6 +273,9 @@ struct ClusterParams {
 int launch_rollout_generic(cev_handle* h, const GenericParams& p, cudaStream_t stream);
 int launch_rollout_cluster(cev_handle* h, const ClusterParams& p, cudaStream_t stream);
 int rollout_cluster_max_clusters(int device);
+int launch_deepqn_fc_tc(cev_handle* h, const float* members, int64_t pitch, int P, int B, int n_act, int f1w_off,
+                        int f1b_off, int ow_off, int ob_off, const float* act3, float* logits, int32_t* actions,
+                        cudaStream_t stream);
 int launch_fc_forward(cev_handle* h, const float* W, int64_t pitch, int in_dim, const int32_t* idx,
                       const float* obs, int64_t N, float* logits, int32_t* actions, int32_t* status,
                       cudaStream_t stream);

@@ -15,6 +15,9 @@
 // makes the kernel HBM-bound on weight bytes at small frames-per-member (roofline
 // in DESIGN.md section 6).  The tcgen05/TMA implicit-GEMM version of the four
 // contractions is the round-2 item for this kernel.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace cev {
@@ -154,6 +157,7 @@ struct DqnParams {
     float* act3;       // [P][B][3136]
     float* logits;
     int32_t* actions;
+    int skip_fc;       // 1: the tensor-core stage (deepqn_tc.cu) computes fc1 / output / argmax
 };
 
 template <int CIN>
@@ -221,7 +225,7 @@ __global__ void __launch_bounds__(DQ_T, 1) deepqn_forward_kernel(const DqnParams
             }
         }
         // ---------------- fc1 (3136 -> 512) + ReLU, out (512 -> A), argmax ---------------
-        for (int f0 = 0; f0 < p.B; f0 += DQ_FB) {
+        for (int f0 = 0; f0 < p.B && !p.skip_fc; f0 += DQ_FB) {
             const int nb = min(DQ_FB, p.B - f0);
             float* x_s = reinterpret_cast<float*>(dq_smem);                   // [DQ_FB][3136]
             float* h_s = x_s + DQ_FB * 3136;                                  // [DQ_FB][512]
@@ -334,6 +338,10 @@ extern "C" int cev_deepqn_forward(cev_handle* h, const float* members, int P, in
     p.act3 = p.act2 + per * 5184;
     p.logits = logits;
     p.actions = actions;
+    // fully-connected stage: tcgen05 (TF32, default) or the fp32 CUDA-core loop (COEVONET_DQN_FC=fp32)
+    const char* fc_env = getenv("COEVONET_DQN_FC");
+    const bool use_tc = !(fc_env && strcmp(fc_env, "fp32") == 0);
+    p.skip_fc = use_tc ? 1 : 0;
     const size_t smem = dqn_smem_bytes(c_in);
     const int grid = P < h->n_sm ? P : h->n_sm;
     if (c_in == 4) {
@@ -343,5 +351,9 @@ extern "C" int cev_deepqn_forward(cev_handle* h, const float* members, int P, in
         CEV_CUDA(cudaFuncSetAttribute(deepqn_forward_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         deepqn_forward_kernel<6><<<grid, DQ_T, smem, (cudaStream_t)stream>>>(p);
     }
-    return check_cuda(cudaGetLastError(), "deepqn_forward_kernel");
+    CEV_CUDA(cudaGetLastError());
+    if (use_tc)
+        return launch_deepqn_fc_tc(h, members, pitch, P, B, n_actions, o.f1w, o.f1b, o.ow, o.ob, p.act3, logits,
+                                   actions, (cudaStream_t)stream);
+    return CEV_OK;
 }

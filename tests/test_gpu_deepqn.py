@@ -1,7 +1,14 @@
 """K2 parity: grouped per-member DeepQN forward (through the C ABI) vs the
 reference's own DeepQN.forward outputs (tests/golden/deepqn.npz) and the oracle.
-Tolerance: fp32 arithmetic with a different summation order -> 2e-5 absolute on
-logits of magnitude ~0.2."""
+
+Two fully-connected stages are tested:
+* ``fp32`` (COEVONET_DQN_FC=fp32): CUDA-core fp32, different summation order only
+  -> 2e-5 absolute on logits of magnitude ~0.2;
+* ``tc`` (default): tcgen05 kind::tf32 (10-bit mantissa inputs, fp32 accumulate over
+  K = 3136) -> 2e-3 absolute; actions are compared where the reference's top-2 logit
+  gap exceeds that tolerance."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -19,29 +26,47 @@ def _pad(rows, c_in, n_act):
     return torch.from_numpy(out).cuda()
 
 
+FC_MODES = {"fp32": 2e-5, "tc": 2e-3}
+
+
+@pytest.fixture(params=sorted(FC_MODES))
+def fc_mode(request):
+    old = os.environ.get("COEVONET_DQN_FC")
+    os.environ["COEVONET_DQN_FC"] = request.param
+    yield request.param
+    if old is None:
+        os.environ.pop("COEVONET_DQN_FC", None)
+    else:
+        os.environ["COEVONET_DQN_FC"] = old
+
+
 @pytest.mark.parametrize("c_in,n_act", [(4, 6), (4, 18), (6, 18)])
-def test_deepqn_forward_matches_reference_golden(golden, c_in, n_act):
+def test_deepqn_forward_matches_reference_golden(golden, fc_mode, c_in, n_act):
     from coevonet_b200 import ops
+    tol = FC_MODES[fc_mode]
     g = golden("deepqn")
     rows = weights.make_dqn_rows(2, c_in, n_act, 600 + c_in + n_act, bn_jitter=float(g["bn_jitter"]))
     rng = np.random.Generator(np.random.PCG64(int(g["frame_seed"])))
     frames = rng.integers(0, 256, (2, 2, c_in, 84, 84), dtype=np.uint8)
     logits, actions = ops.deepqn_forward(_pad(rows, c_in, n_act), torch.from_numpy(frames).cuda(), c_in, n_act)
     want = g[f"c{c_in}a{n_act}.logits"]
-    np.testing.assert_allclose(logits.cpu().numpy(), want, rtol=0, atol=2e-5)
-    assert np.array_equal(actions.cpu().numpy(), np.argmax(want, axis=-1))
+    np.testing.assert_allclose(logits.cpu().numpy(), want, rtol=0, atol=tol)
+    srt = np.sort(want, axis=-1)
+    safe = (srt[..., -1] - srt[..., -2]) > 2 * tol
+    assert np.array_equal(actions.cpu().numpy()[safe], np.argmax(want, axis=-1)[safe])
 
 
-def test_deepqn_many_frames_and_members_vs_oracle():
+def test_deepqn_many_frames_and_members_vs_oracle(fc_mode):
     from coevonet_b200 import ops
+    tol = FC_MODES[fc_mode]
     c_in, n_act, P, B = 4, 6, 3, 13                      # B > frames-per-fc-pass exercises chunking
     rows = weights.make_dqn_rows(P, c_in, n_act, 91, bn_jitter=0.1)
     frames = ops.random_frames(5, (P, B, c_in, 84, 84), "cuda")
     logits, actions = ops.deepqn_forward(_pad(rows, c_in, n_act), frames, c_in, n_act)
     want, want_act = odqn.dqn_forward_batch(rows, frames.cpu().numpy(), c_in, n_act)
-    np.testing.assert_allclose(logits.cpu().numpy(), want, rtol=0, atol=3e-5)
+    np.testing.assert_allclose(logits.cpu().numpy(), want, rtol=0, atol=1.5 * tol)
     srt = np.sort(want, axis=-1)
-    safe = (srt[..., -1] - srt[..., -2]) > 1e-4
+    safe = (srt[..., -1] - srt[..., -2]) > 4 * tol
     assert np.array_equal(actions.cpu().numpy()[safe], want_act[safe])
     # per-frame BatchNorm: a frame's logits do not depend on its batch neighbours
     solo, _ = ops.deepqn_forward(_pad(rows, c_in, n_act)[1:2].contiguous(), frames[1:2, 4:5].contiguous(), c_in, n_act)
@@ -58,5 +83,7 @@ def test_deepqn_module_dropin():
     from oracle import layout as olayout
     row = olayout.pack_dqn_state_dict(sd, 4, 6)
     want, _ = odqn.dqn_forward_batch(row[None], x.numpy().astype(np.uint8)[None], 4, 6)
-    np.testing.assert_allclose(got.numpy(), want[0], rtol=0, atol=3e-5)
-    assert net.determine_action(x[:1]) == int(np.argmax(want[0, 0]))
+    np.testing.assert_allclose(got.numpy(), want[0], rtol=0, atol=3e-3)
+    srt = np.sort(want[0, 0])
+    if srt[-1] - srt[-2] > 6e-3:
+        assert net.determine_action(x[:1]) == int(np.argmax(want[0, 0]))
