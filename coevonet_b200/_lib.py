@@ -64,6 +64,7 @@ _SIGNATURES = {
                                        c_void_p, c_void_p]),
     "cev_deepqn_forward": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_int, c_int,
                                    c_int, c_void_p, c_void_p, c_void_p]),
+    "cev_fc_init_f32": (c_int, [c_void_p, c_int, c_uint64, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "cev_init_states_f64": (c_int, [c_void_p, c_uint64, c_uint32, c_int64, c_int64, c_void_p, c_void_p]),
     "cev_random_frames_u8": (c_int, [c_void_p, c_uint64, c_int64, c_void_p, c_void_p]),
     "cev_philox_words": (c_int, [c_void_p, c_uint64, c_int, c_int, c_uint32, c_int64, c_int64,

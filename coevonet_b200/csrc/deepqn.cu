@@ -52,12 +52,21 @@ __host__ __device__ inline DqnOffsets dqn_offsets(int c_in, int n_act) {
     return o;
 }
 
-// stage conv weights W[cout][k] (global, k contiguous) as Wt[k][cout] in shared memory
+// stage conv weights W[cout][k] (global, k contiguous) as Wt[k][cout] in shared memory through
+// a padded [COUT][33] tile: global reads are coalesced along k, both shared-memory sides
+// are bank-conflict free.  K is a multiple of 32 for all three layers (256|384, 512, 576).
 template <int COUT>
-__device__ __forceinline__ void stage_weights_transposed(const float* __restrict__ w, int K, float* wt) {
-    for (int i = threadIdx.x; i < COUT * K; i += DQ_T) {
-        const int c = i / K, k = i - c * K;
-        wt[k * COUT + c] = __ldg(w + i);
+__device__ __forceinline__ void stage_weights_transposed(const float* __restrict__ w, int K, float* wt,
+                                                         float* tile /*[COUT][33]*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int kb = 0; kb < K; kb += 32) {
+        for (int c = warp; c < COUT; c += DQ_T / 32) tile[c * 33 + lane] = __ldg(w + (size_t)c * K + kb + lane);
+        __syncthreads();
+        for (int i = threadIdx.x; i < 32 * COUT; i += DQ_T) {
+            const int c = i % COUT, kk = i / COUT;
+            wt[(kb + kk) * COUT + c] = tile[c * 33 + kk];
+        }
+        __syncthreads();
     }
 }
 
@@ -176,8 +185,9 @@ __global__ void __launch_bounds__(DQ_T, 1) deepqn_forward_kernel(const DqnParams
             float* out_s = wt + CIN * 64 * 32;                                // [32][400]
             float* lut = out_s + 12800;                                       // [256]
             uint8_t* in_s = reinterpret_cast<uint8_t*>(lut + 256);            // [CIN][84][84]
+            float* tile = reinterpret_cast<float*>(in_s + CIN * 7056);        // [32][33]
             __syncthreads();
-            stage_weights_transposed<32>(W + o.c1w, CIN * 64, wt);
+            stage_weights_transposed<32>(W + o.c1w, CIN * 64, wt, tile);
             for (int i = threadIdx.x; i < 256; i += DQ_T) lut[i] = __fdiv_rn((float)i, 255.0f);
             for (int f = 0; f < p.B; ++f) {
                 const uint8_t* fr = p.frames + ((int64_t)m * p.B + f) * CIN * 7056;
@@ -195,8 +205,9 @@ __global__ void __launch_bounds__(DQ_T, 1) deepqn_forward_kernel(const DqnParams
             float* wt = reinterpret_cast<float*>(dq_smem);                    // [512][64]
             float* in_s = wt + 512 * 64;                                      // [32][400]
             float* out_s = in_s + 12800;                                      // [64][81]
+            float* tile = out_s + 5184;                                       // [64][33]
             __syncthreads();
-            stage_weights_transposed<64>(W + o.c2w, 512, wt);
+            stage_weights_transposed<64>(W + o.c2w, 512, wt, tile);
             for (int f = 0; f < p.B; ++f) {
                 __syncthreads();
                 for (int i = threadIdx.x; i < 12800 / 4; i += DQ_T)
@@ -212,8 +223,9 @@ __global__ void __launch_bounds__(DQ_T, 1) deepqn_forward_kernel(const DqnParams
             float* wt = reinterpret_cast<float*>(dq_smem);                    // [576][64]
             float* in_s = wt + 576 * 64;                                      // [64][81]
             float* out_s = in_s + 5184;                                       // [64][49]
+            float* tile = out_s + 3136;                                       // [64][33]
             __syncthreads();
-            stage_weights_transposed<64>(W + o.c3w, 576, wt);
+            stage_weights_transposed<64>(W + o.c3w, 576, wt, tile);
             for (int f = 0; f < p.B; ++f) {
                 __syncthreads();
                 for (int i = threadIdx.x; i < 5184 / 4; i += DQ_T)
@@ -291,9 +303,9 @@ __global__ void __launch_bounds__(DQ_T, 1) deepqn_forward_kernel(const DqnParams
 }
 
 static size_t dqn_smem_bytes(int c_in) {
-    const size_t conv1 = (size_t)(c_in * 64 * 32 + 12800 + 256) * 4 + (size_t)c_in * 7056;
-    const size_t conv2 = (size_t)(512 * 64 + 12800 + 5184) * 4;
-    const size_t conv3 = (size_t)(576 * 64 + 5184 + 3136) * 4;
+    const size_t conv1 = (size_t)(c_in * 64 * 32 + 12800 + 256 + 32 * 33) * 4 + (size_t)c_in * 7056;
+    const size_t conv2 = (size_t)(512 * 64 + 12800 + 5184 + 64 * 33) * 4;
+    const size_t conv3 = (size_t)(576 * 64 + 5184 + 3136 + 64 * 33) * 4;
     const size_t fc = (size_t)(DQ_FB * 3136 + DQ_FB * 512) * 4;
     size_t m = conv1 > conv2 ? conv1 : conv2;
     m = m > conv3 ? m : conv3;

@@ -247,6 +247,38 @@ __global__ void __launch_bounds__(PT) init_states_kernel(uint32_t k0, uint32_t k
     for (int i = 0; i < 10; ++i) o[1 + i] = u_pm1(w[1 + i]);
 }
 
+// Founder initialisation on the device (create_agent -> FCNetwork default init,
+// MPE/fcnetwork.py:11-22): nn.Linear weight and bias ~ U(-1/sqrt(fan_in), 1/sqrt(fan_in)),
+// LayerNorm gamma = 1, beta = 0.  Same distribution as PyTorch's default, Philox stream
+// (kind 4) instead of torch's global generator; needed when P is too large to build
+// 3*P nn.Modules on the host.
+__global__ void __launch_bounds__(PT) fc_init_kernel(int in_dim, int64_t pitch, uint32_t k0, uint32_t k1,
+                                                     uint32_t tag, int64_t row0, float* __restrict__ out) {
+    const FcOffsets o = fc_offsets(in_dim);
+    const int64_t r = blockIdx.x;
+    const int j4 = blockIdx.y * PT + threadIdx.x;
+    if ((int64_t)j4 * 4 >= pitch) return;
+    const U4 w = philox4x32_10(U4{(uint32_t)j4, (uint32_t)(row0 + r), 0u, tag}, k0, k1);
+    const uint32_t x[4] = {w.x, w.y, w.z, w.w};
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int j = j4 * 4 + i;
+        if (j >= o.total) v[i] = 0.f;
+        else if (j >= o.ln1g && j < o.ln1b) v[i] = 1.f;
+        else if (j >= o.ln1b && j < o.fc2w) v[i] = 0.f;
+        else if (j >= o.ln2g && j < o.ln2b) v[i] = 1.f;
+        else if (j >= o.ln2b && j < o.outw) v[i] = 0.f;
+        else {
+            const int fan_in = j < o.ln1g ? in_dim : (j < o.ln2g ? H1 : H2);
+            const double bound = 1.0 / sqrt((double)fan_in);
+            const double u = ((double)x[i] + 0.5) * (2.0 / 4294967296.0) - 1.0;
+            v[i] = (float)(u * bound);
+        }
+    }
+    *reinterpret_cast<float4*>(out + r * pitch + (int64_t)j4 * 4) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
 __global__ void __launch_bounds__(PT) random_frames_kernel(uint32_t k0, uint32_t k1, int64_t n16,
                                                            uint4* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * PT + threadIdx.x;
@@ -407,6 +439,20 @@ int cev_diversity_dist_f32(cev_handle* h, const float* pop, int64_t n_rows, int6
     if (n_rows <= 0) return CEV_OK;
     diversity_dist_kernel<<<(unsigned)n_rows, PT, 0, (cudaStream_t)stream>>>(pop, pitch, ref, in_dim, dist);
     return check_cuda(cudaGetLastError(), "diversity_dist_kernel");
+}
+
+int cev_fc_init_f32(cev_handle* h, int in_dim, uint64_t seed, int role, int64_t row0, int64_t n_rows,
+                    int64_t pitch, float* out, cev_stream stream) {
+    CEV_REQUIRE(h && out, "fc_init: null pointer");
+    CEV_REQUIRE(in_dim == IN_ADV || in_dim == IN_GOOD, "fc_init: in_dim must be 8 or 10");
+    CEV_REQUIRE(pitch >= fc_offsets(in_dim).total && pitch % 4 == 0 && aligned16(out), "fc_init: bad pitch / alignment");
+    CEV_REQUIRE(row0 >= 0 && n_rows >= 0 && row0 + n_rows <= 0xFFFFFFFFll, "fc_init: bad row range");
+    if (n_rows == 0) return CEV_OK;
+    uint32_t k0, k1;
+    split_seed(seed, k0, k1);
+    dim3 grid((unsigned)n_rows, (unsigned)((pitch / 4 + PT - 1) / PT));
+    fc_init_kernel<<<grid, PT, 0, (cudaStream_t)stream>>>(in_dim, pitch, k0, k1, noise_tag(4, role), row0, out);
+    return check_cuda(cudaGetLastError(), "fc_init_kernel");
 }
 
 int cev_init_states_f64(cev_handle* h, uint64_t seed, uint32_t stream_id, int64_t rec0, int64_t n, double* out,

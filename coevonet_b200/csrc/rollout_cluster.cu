@@ -13,8 +13,12 @@
 //    cluster of 4 CTAs each keeps a 64-row quarter (128 KB) RESIDENT in shared
 //    memory for the whole tile: member weights leave HBM once per tile, not
 //    once per step.
-//  * Opponent weights (shared by every tile, L2-resident) are streamed through
-//    a 3-stage cp.async ring, 64 rows x 32 k per stage.
+//  * Opponent weights (shared by every tile, L2-resident) are repacked once per
+//    launch into pre-swizzled 4 KB chunk images and streamed by TMA bulk copies
+//    (cp.async.bulk + mbarrier complete_tx) into 12 slots (6 dedicated + 6 borrowed
+//    from the idle W1 arena).  Each 16-k chunk has exactly one consumer warp, which
+//    refills the slot it drained; two alternating "full" mbarriers per slot keep the
+//    parity waits unambiguous.  No CTA-wide barrier inside the fc2 loop.
 //  * Per cycle the three seats' forwards are independent (same world state):
 //    each CTA computes layer 1 + LayerNorm redundantly (K <= 10, cheap), its
 //    quarter of fc2 for all BT env instances with packed FFMA2 on k-pairs,
@@ -83,8 +87,8 @@ struct SmemLayout {
     static constexpr size_t off_plog = off_lnx + (size_t)3 * CL * BT * 8;
     static constexpr size_t off_act = off_plog + (size_t)3 * CL * NACT * BT * 4;
     static constexpr size_t off_flag = off_act + (size_t)3 * BT * 8;
-    static constexpr size_t off_bar = off_flag + 16;             // full[NSLOT], w1_full
-    static constexpr size_t total = off_bar + 128;
+    static constexpr size_t off_bar = off_flag + 16;             // full[NSLOT][2], w1_full
+    static constexpr size_t total = off_bar + 256;
 };
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
@@ -315,7 +319,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t n) {
     if (mbar_try_wait(bar, n & 1)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, n & 1)) {
-        if (clock64() - t0 > 4000000000LL) __trap();
+        if (clock64() - t0 > 4000000000LL) {
+#ifdef CEV_PROFILE
+            // development build: record who timed out and carry on (results are then invalid)
+            cev_prof_acc[15] = 0xDEAD0000ull | (unsigned long long)(smem_u32(bar) & 0xFFFF);
+            cev_prof_acc[14] = n;
+            cev_prof_acc[13] = ((unsigned long long)blockIdx.x << 32) | threadIdx.x;
+            return;
+#else
+            __trap();
+#endif
+        }
     }
 }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
@@ -365,8 +379,8 @@ rollout_cluster_kernel(const ClusterParams p) {
     int* act_s = reinterpret_cast<int*>(smem + L::off_act);        // [3][BT]
     float* gap_s = reinterpret_cast<float*>(act_s + 3 * BT);       // [3][BT]
     int* flag = reinterpret_cast<int*>(smem + L::off_flag);
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + L::off_bar);   // [NSLOT]
-    uint64_t* bar_w1 = bar_full + NSLOT;
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + L::off_bar);   // [NSLOT][2]
+    uint64_t* bar_w1 = bar_full + 2 * NSLOT;
 
     cg::cluster_group cluster = cg::this_cluster();
     const int q = (int)cluster.block_rank();
@@ -378,7 +392,7 @@ rollout_cluster_kernel(const ClusterParams p) {
 
     if (t == 0) {
         *flag = 0;
-        for (int i = 0; i < NSLOT; ++i) mbar_init(bar_full + i, 1);   // one arrive.expect_tx per fill
+        for (int i = 0; i < 2 * NSLOT; ++i) mbar_init(bar_full + i, 1);   // one arrive.expect_tx per fill
         mbar_init(bar_w1, 1);
         mbar_fence_init();
     }
@@ -469,12 +483,19 @@ rollout_cluster_kernel(const ClusterParams p) {
                         // ---- streamed seats: a slot is one 4 KB chunk image; chunk ch lives in slot
                         //      ch % 12 (6 dedicated + 6 borrowed from the W1 arena once layer 1 is done)
                         const float4* src = wpack[s];
+                        // Successive uses of a slot have DIFFERENT consumer warps, and a parity wait can
+                        // only tell "current phase done or not": with one barrier per slot, a warp running
+                        // a round ahead would pass its wait for use u+1 while use u is still in flight.
+                        // Two barriers per slot, alternating by use, make every wait unambiguous (the
+                        // same warp consumes uses u and u+2 of a slot).
                         auto issue = [&](int ch) {
                             const int sl = ch % NSLOT;
+                            const uint32_t use = sp * (sl < 8 ? 3u : 2u) + (uint32_t)(ch / NSLOT);
+                            uint64_t* bar = bar_full + 2 * sl + (use & 1);
                             float4* dst = sl < NSLOT_D ? stage + sl * STAGE_F4
                                                        : reinterpret_cast<float4*>(w1a) + (sl - NSLOT_D) * STAGE_F4;
-                            mbar_arrive_expect_tx(bar_full + sl, STAGE_BYTES);
-                            bulk_g2s(dst, src + (size_t)ch * STAGE_F4, STAGE_BYTES, bar_full + sl);
+                            mbar_arrive_expect_tx(bar, STAGE_BYTES);
+                            bulk_g2s(dst, src + (size_t)ch * STAGE_F4, STAGE_BYTES, bar);
                         };
                         auto issue_w1 = [&](int seat) {
                             const uint32_t bytes = (uint32_t)(H1 * seat_in_dim(seat) + 3 * H1) * 4;
@@ -526,7 +547,7 @@ rollout_cluster_kernel(const ClusterParams p) {
                                 const int ch = warp + NW * r;
                                 const int sl = ch % NSLOT;
                                 const uint32_t use = sp * (sl < 8 ? 3u : 2u) + (uint32_t)(ch / NSLOT);
-                                if (!DBG_FLAG(3)) mbar_wait(bar_full + sl, use);
+                                if (!DBG_FLAG(3)) mbar_wait(bar_full + 2 * sl + (use & 1), use >> 1);
                                 const float4* wst = sl < NSLOT_D ? stage + sl * STAGE_F4
                                                                  : reinterpret_cast<const float4*>(w1a) + (sl - NSLOT_D) * STAGE_F4;
                                 fc2_chunk<BT, true>(wst, 0, u, ch * KCH, acc);

@@ -94,18 +94,29 @@ def genetic_algorithm_train(env, agent, args, output_dir):
     from .utils.game_logic_functions import _device
     dev = _device()
     comm = _engine.Comm()
-    hof_agents, pop_agents = build_initial_state(env, args)
-    for name, role in (("agent_0", "agent_1"), ("agent_1", "agent_0"), ("adversary", "adversary_0")):
-        n_par = sum(p.numel() for p in hof_agents[role][0].model.parameters())
-        print(f"\nNumber of parameters for {name} network: {n_par}")
-
     shard = _engine.Shard(args.population, comm.rank, comm.world)
     sl = slice(shard.row0, shard.row0 + shard.n_local)
-    pop_rows = {r: layout.pack_models([a.model for a in pop_agents[r][sl]], layout.OBS_DIM[r]) for r in ROLES}
-    hof_rows = {r: layout.pack_models([a.model for a in hof_agents[r]], layout.OBS_DIM[r]) for r in ROLES}
-    # Appendix C #3: diversity is measured against the LAST founder created for each role
-    founder = {r: layout.pack_models([pop_agents[r][-1].model], layout.OBS_DIM[r])[0] for r in ROLES}
-    del pop_agents
+    if getattr(args, "device_init", False):
+        # founders drawn on the device (same distribution as PyTorch's default init, Philox
+        # stream, global member ids): no 3*P nn.Module constructions on the host
+        from . import ops
+        seed, P, H = getattr(args, "seed", 1870300), args.population, args.hof_size
+        pop_rows = {r: ops.fc_init(layout.OBS_DIM[r], seed, r, shard.row0, shard.n_local, dev) for r in ROLES}
+        hof_rows = {r: ops.fc_init(layout.OBS_DIM[r], seed, r, P, H, dev) for r in ROLES}
+        # Appendix C #3: diversity is measured against the LAST founder created for each role
+        founder = {r: ops.fc_init(layout.OBS_DIM[r], seed, r, P - 1, 1, dev)[0] for r in ROLES}
+        for name, role in (("agent_0", "agent_1"), ("agent_1", "agent_0"), ("adversary", "adversary_0")):
+            print(f"\nNumber of parameters for {name} network: {layout.fc_dim(layout.OBS_DIM[role])}")
+    else:
+        hof_agents, pop_agents = build_initial_state(env, args)
+        for name, role in (("agent_0", "agent_1"), ("agent_1", "agent_0"), ("adversary", "adversary_0")):
+            n_par = sum(p.numel() for p in hof_agents[role][0].model.parameters())
+            print(f"\nNumber of parameters for {name} network: {n_par}")
+        pop_rows = {r: layout.pack_models([a.model for a in pop_agents[r][sl]], layout.OBS_DIM[r]) for r in ROLES}
+        hof_rows = {r: layout.pack_models([a.model for a in hof_agents[r]], layout.OBS_DIM[r]) for r in ROLES}
+        # Appendix C #3: diversity is measured against the LAST founder created for each role
+        founder = {r: layout.pack_models([pop_agents[r][-1].model], layout.OBS_DIM[r])[0] for r in ROLES}
+        del pop_agents
     eng = _engine.GAEngine(args, dev, pop_rows, hof_rows, founder, env=env, comm=comm)
 
     rewards = {r: [] for r in ROLES}

@@ -58,6 +58,9 @@ def parse_arguments(argv=None):
                         "correctly (see DESIGN.md, reference quirks)")
     p.add_argument("--init_states", choices=["reference", "device"], default="reference",
                    help="initial env states: the reference's host PCG64 stream, or Philox on the GPU")
+    p.add_argument("--device_init", action="store_true",
+                   help="draw the GA founders on the device (Philox; same distribution as PyTorch's default "
+                        "init) instead of building 3*P nn.Modules on the host; implied for population > 4096")
     p.add_argument("--seed", type=int, default=1870300, help="run seed of the Philox noise streams")
     p.add_argument("--torch_seed", type=int, default=None, help="torch.manual_seed for the founders")
     p.add_argument("--no_plots", action="store_true")
@@ -107,6 +110,10 @@ class Args:
         self.envs_per_member = a.envs_per_member
         self.reference_compat = not a.no_reference_compat
         self.init_states = a.init_states
+        self.device_init = a.device_init or a.population > 4096
+        if a.population > 4096 and a.init_states == "reference":
+            # the host PCG64 stream costs ~5 us per reset; at this scale draw the states on the device
+            self.init_states = "device"
         self.seed = a.seed
         self.plots = not a.no_plots
 

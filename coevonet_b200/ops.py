@@ -266,6 +266,19 @@ def deepqn_forward(members, frames, c_in, n_actions):
     return logits, actions
 
 
+def fc_init(in_dim, seed, role, row0, n_rows, device, *, out=None):
+    """Device-side founders: float32[n_rows, pitch] rows with PyTorch's default-init
+    distribution (Philox stream; global member ids row0 .. row0+n_rows-1)."""
+    pitch = layout.fc_pitch(in_dim)
+    if out is None:
+        out = torch.empty((n_rows, pitch), dtype=torch.float32, device=device)
+    dev = _need_cuda(out)
+    role_id = layout.ROLE_ID[role] if isinstance(role, str) else int(role)
+    check(_call("cev_fc_init_f32", handle(dev.index), int(in_dim), int(seed), role_id, int(row0), int(n_rows),
+                pitch, _ptr(out), _stream(dev)), "cev_fc_init_f32")
+    return out
+
+
 def init_states(seed, stream_id, n, device, rec0=0):
     """Device-generated initial env states fp64[n,11] (Appendix A.3 distribution):
     records rec0 .. rec0+n-1 of Philox stream ``stream_id``."""

@@ -52,6 +52,7 @@ typedef void* cev_stream;               /* cudaStream_t */
 #define CEV_KIND_GA 1
 #define CEV_KIND_ENV 2
 #define CEV_KIND_FRAMES 3
+#define CEV_KIND_INIT 4
 
 int cev_version(void);
 const char* cev_last_error(void);
@@ -193,6 +194,15 @@ int cev_diversity_dist_f32(cev_handle* h, const float* pop, int64_t n_rows,
 int cev_deepqn_forward(cev_handle* h, const float* members, int P, int64_t pitch,
                        const uint8_t* frames, int B, int c_in, int n_actions,
                        float* logits, int32_t* actions, cev_stream stream);
+
+/*
+ * Founder initialisation on the device.  Replaces create_agent -> MPEAgent -> FCNetwork
+ * default init (utils/game_logic_functions.py:58-64, MPE/fcnetwork.py:11-22) for rows
+ * [row0, row0+n_rows): Linear weight/bias ~ U(-1/sqrt(fan_in), 1/sqrt(fan_in)), LayerNorm
+ * gamma = 1, beta = 0, Philox(seed, INIT, role, member, param).
+ */
+int cev_fc_init_f32(cev_handle* h, int in_dim, uint64_t seed, int role, int64_t row0, int64_t n_rows,
+                    int64_t pitch, float* out, cev_stream stream);
 
 /* device-side synthetic inputs (bench / tests): initial env states drawn
  * U(-1,1)^2 + goal in {0,1} (Appendix A.3 distribution, Philox stream; records

@@ -30,6 +30,7 @@ KIND_ES = 0       # ES perturbation noise (agent.py:31-70 replacement)
 KIND_GA = 1       # GA mutation noise     (agent.py:25-29 replacement)
 KIND_ENV = 2      # device-side initial env states (Appendix A.3 replacement)
 KIND_FRAMES = 3   # synthetic Atari frames
+KIND_INIT = 4     # device-side founder initialisation
 
 ROLE_ID = {"agent_0": 0, "agent_1": 1, "adversary_0": 2}
 
@@ -113,4 +114,24 @@ def init_states(seed, stream_id, n, rec0=0):
     out[:, 0] = (w[0] & np.uint32(1)).astype(np.float64)
     for i in range(10):
         out[:, 1 + i] = (w[1 + i].astype(np.float64) + 0.5) * (2.0 / 4294967296.0) - 1.0
+    return out
+
+
+def fc_init_rows(seed, role, members, in_dim):
+    """fp32[len(members), D] founders, bit-exact restatement of ``cev_fc_init_f32``:
+    Linear ~ U(-1/sqrt(fan_in), 1/sqrt(fan_in)) from one Philox word per parameter,
+    LayerNorm gamma = 1, beta = 0 (PyTorch default init of MPE/fcnetwork.py:11-22)."""
+    from . import layout
+    segs, total = layout.fc_segments(in_dim)
+    w = words(seed, KIND_INIT, role, 0, members, (total + 3) // 4).reshape(len(members), -1)[:, :total]
+    u = (w.astype(np.float64) + 0.5) * (2.0 / 4294967296.0) - 1.0
+    out = np.zeros((len(members), total), dtype=np.float32)
+    fan = {"fc1": in_dim, "fc2": layout.H1, "output": layout.H2}
+    for name, off, shape, _ in segs:
+        n = int(np.prod(shape))
+        mod, kind = name.split(".")
+        if mod.startswith("ln"):
+            out[:, off:off + n] = 1.0 if kind == "weight" else 0.0
+        else:
+            out[:, off:off + n] = (u[:, off:off + n] * (1.0 / np.sqrt(float(fan[mod])))).astype(np.float32)
     return out

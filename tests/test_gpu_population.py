@@ -139,6 +139,20 @@ def test_select_topk_bit_exact(golden):
         assert np.array_equal(got, ga_es.select_topk(v, k)), (P, k)
 
 
+@pytest.mark.parametrize("role,in_dim", [("agent_0", 10), ("adversary_0", 8)])
+def test_fc_init_bit_exact(role, in_dim):
+    from coevonet_b200 import layout, ops
+    D = layout.fc_dim(in_dim)
+    got = ops.fc_init(in_dim, SEED, role, 5, 4, "cuda").cpu().numpy()
+    want = philox.fc_init_rows(SEED, philox.ROLE_ID[role], np.arange(5, 9), in_dim)
+    assert np.array_equal(got[:, :D], want)
+    assert np.all(got[:, D:] == 0)
+    segs, _ = olayout.fc_segments(in_dim)
+    off = {n: o for n, o, _, _ in segs}
+    w2 = got[:, off["fc2.weight"]:off["fc2.bias"]]
+    assert abs(w2.std() - (1 / np.sqrt(512)) / np.sqrt(3)) < 2e-4 and np.abs(w2).max() <= 1 / np.sqrt(512)
+
+
 def test_gather_rows_and_axpy():
     from coevonet_b200 import ops
     src = torch.randn((9, 64), device="cuda")

@@ -194,3 +194,27 @@ def test_full_size_properties():
     # rewards are bounded by geometry: |r| <= 25 * (2*sqrt(2) + drift)
     assert torch.isfinite(out1).all()
     assert (out1[..., 2] <= 0).all()
+
+
+def test_large_population_stress_is_deterministic():
+    """BASELINE config-3 scale per GPU (tens of thousands of members, hof = 3): two runs of
+    ~150 k tiles must complete and agree bit for bit.  (Regression: a parity-aliased mbarrier
+    wait in the streamed-operand pipeline only misfired at this scale.)"""
+    from coevonet_b200 import ops
+    P, K = 49152, 3
+    pop = ops.fc_init(10, 7, "agent_0", 0, P, "cuda")
+    adv = ops.fc_init(8, 7, "adversary_0", P, K, "cuda")
+    a1 = ops.fc_init(10, 7, "agent_1", P, K, "cuda")
+    init = ops.init_states(7, 0, P * K, "cuda").reshape(P, K, 1, 11)
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    out1 = ops.mpe_rollout("agent_0", pop, adv, a1, init, status=status)
+    out2 = ops.mpe_rollout("agent_0", pop, adv, a1, init, status=status)
+    torch.cuda.synchronize()
+    assert int(status.item()) == 0
+    assert torch.equal(out1, out2)
+    # spot-check 4 members against the oracle
+    sel = [0, 12345, 30000, P - 1]
+    nets = {"agent_0": pop[sel].cpu().numpy(), "agent_1": a1.cpu().numpy(), "adversary_0": adv.cpu().numpy()}
+    idx = np.array([[k, i, k] for i in range(len(sel)) for k in range(K)])
+    ref = orollout.rollout(nets, idx, init[sel].cpu().numpy().reshape(-1, 11))
+    _compare(out1[sel].cpu().numpy().reshape(-1, 4), ref, "large-population sample")
