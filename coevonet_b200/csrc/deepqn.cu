@@ -52,21 +52,15 @@ __host__ __device__ inline DqnOffsets dqn_offsets(int c_in, int n_act) {
     return o;
 }
 
-// stage conv weights W[cout][k] (global, k contiguous) as Wt[k][cout] in shared memory through
-// a padded [COUT][33] tile: global reads are coalesced along k, both shared-memory sides
-// are bank-conflict free.  K is a multiple of 32 for all three layers (256|384, 512, 576).
+// stage conv weights W[cout][k] (global, k contiguous) as Wt[k][cout] in shared memory.
+// (A padded-tile transposition that removes the shared-memory store conflicts was measured
+// slower -- two block barriers per 32-k tile -- so the direct form stays.)
 template <int COUT>
 __device__ __forceinline__ void stage_weights_transposed(const float* __restrict__ w, int K, float* wt,
-                                                         float* tile /*[COUT][33]*/) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int kb = 0; kb < K; kb += 32) {
-        for (int c = warp; c < COUT; c += DQ_T / 32) tile[c * 33 + lane] = __ldg(w + (size_t)c * K + kb + lane);
-        __syncthreads();
-        for (int i = threadIdx.x; i < 32 * COUT; i += DQ_T) {
-            const int c = i % COUT, kk = i / COUT;
-            wt[(kb + kk) * COUT + c] = tile[c * 33 + kk];
-        }
-        __syncthreads();
+                                                         float* /*tile, unused*/) {
+    for (int i = threadIdx.x; i < COUT * K; i += DQ_T) {
+        const int c = i / K, k = i - c * K;
+        wt[k * COUT + c] = __ldg(w + i);
     }
 }
 
