@@ -194,13 +194,21 @@ class GAEngine(_EngineBase):
         limit = a.max_timesteps_per_episode
         opp_a, opp_b = self._opponents(role)
         init = self._initial_states(self.P, K, self.shard, ROLES.index(role) + 4 * self.gen)
+        if self.compat and not getattr(a, "play_discarded_hof_games", False):
+            # The reference plays hof_size games per member but OVERWRITES the reward each time
+            # (`=`, genetic_algorithm.py:140,172,205; Appendix C #2): only the game against the
+            # oldest HoF entry (k = K-1) reaches the fitness.  The discarded games are not
+            # simulated here; their initial-state records are still drawn (above), so the game
+            # that counts starts from the same state as in a reference run.
+            opp_a, opp_b = opp_a[K - 1:K].contiguous(), opp_b[K - 1:K].contiguous()
+            init = init[:, K - 1:K].contiguous()
         out = self.k.mpe_rollout(role, self.pop[role], opp_a, opp_b, init, n_cycles=_limit_cycles(self.k, limit),
                                  pos_first=self.pos_first, status=self.status)
-        slot = self._role_slot(out, role, limit)                      # [n_local, K, E]
+        slot = self._role_slot(out, role, limit)                      # [n_local, K or 1, E]
         if self.compat:
             # only the LAST HoF game counts (reward overwritten, `=`), then / hof_size
             # (genetic_algorithm.py:140-144, Appendix C #2)
-            reward = slot[:, K - 1, :].mean(dim=1) / K
+            reward = slot[:, -1, :].mean(dim=1) / K
         else:
             reward = slot.mean(dim=(1, 2))
         # fitness sharing against the frozen founder (Appendix C #3); applied regardless of

@@ -61,6 +61,9 @@ def parse_arguments(argv=None):
     p.add_argument("--device_init", action="store_true",
                    help="draw the GA founders on the device (Philox; same distribution as PyTorch's default "
                         "init) instead of building 3*P nn.Modules on the host; implied for population > 4096")
+    p.add_argument("--play_discarded_hof_games", action="store_true",
+                   help="GA, reference_compat: also simulate the hof_size-1 games per member whose reward the "
+                        "reference overwrites (they never reach the fitness; skipped by default)")
     p.add_argument("--seed", type=int, default=1870300, help="run seed of the Philox noise streams")
     p.add_argument("--torch_seed", type=int, default=None, help="torch.manual_seed for the founders")
     p.add_argument("--no_plots", action="store_true")
@@ -115,6 +118,7 @@ class Args:
             # the host PCG64 stream costs ~5 us per reset; at this scale draw the states on the device
             self.init_states = "device"
         self.seed = a.seed
+        self.play_discarded_hof_games = a.play_discarded_hof_games
         self.plots = not a.no_plots
 
     def print_attributes(self, args=None):
