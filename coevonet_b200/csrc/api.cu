@@ -53,6 +53,8 @@ int cev_create(int device, cev_handle** out) {
     h->workspace_bytes = 0;
     h->opp_workspace = nullptr;
     h->opp_workspace_bytes = 0;
+    h->ls_workspace = nullptr;
+    h->ls_workspace_bytes = 0;
     int ncl = rollout_cluster_max_clusters(device);
     if (ncl <= 0) ncl = h->n_sm / 4 - 4;
     h->n_clusters = ncl;
@@ -64,6 +66,7 @@ int cev_destroy(cev_handle* h) {
     if (!h) return CEV_OK;
     if (h->workspace) cudaFree(h->workspace);
     if (h->opp_workspace) cudaFree(h->opp_workspace);
+    if (h->ls_workspace) cudaFree(h->ls_workspace);
     delete h;
     return CEV_OK;
 }
@@ -84,10 +87,19 @@ int cev_dqn_dim(int c_in, int n_actions) {
 }
 int cev_dqn_pitch(int c_in, int n_actions) { return round_up(cev_dqn_dim(c_in, n_actions), 32); }
 
+// Which K1 kernel a structured rollout uses: 1 generic, 2 cluster (member weights resident, best when a
+// member plays few episodes: GA), 3 lockstep (opponent forwards on tcgen05, best when every member
+// plays many episodes against shared opponents: ES).
+static int rollout_plan(const cev_handle* h, int P, int K, int E, int variant) {
+    if (variant != 0) return variant;
+    if ((int64_t)P * K * E >= 2048 && K * E >= 8) return 3;
+    return h->n_clusters > 0 ? 2 : 1;
+}
+
 static int check_cfg(const cev_rollout_cfg* cfg) {
     CEV_REQUIRE(cfg != nullptr, "rollout: null cfg");
     CEV_REQUIRE(cfg->n_cycles >= 0 && cfg->n_cycles <= MAX_CYCLES, "rollout: n_cycles must be in [0, %d]", MAX_CYCLES);
-    CEV_REQUIRE(cfg->variant >= 0 && cfg->variant <= 2, "rollout: variant must be 0, 1 or 2");
+    CEV_REQUIRE(cfg->variant >= 0 && cfg->variant <= 3, "rollout: variant must be 0..3");
     return CEV_OK;
 }
 
@@ -109,8 +121,8 @@ int cev_mpe_rollout_f32(cev_handle* h, int member_seat, const float* members, in
     CEV_REQUIRE(aligned16(members) && aligned16(opp_a) && aligned16(opp_b), "mpe_rollout: rows must be 16B aligned");
     if (P == 0) return CEV_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    const bool use_cluster = cfg->variant == 2 || (cfg->variant == 0 && h->n_clusters > 0);
-    if (use_cluster) {
+    const int variant = rollout_plan(h, P, K, E, cfg->variant);
+    if (variant >= 2) {
         ClusterParams p{};
         p.members = members;
         p.member_pitch = member_pitch;
@@ -128,7 +140,7 @@ int cev_mpe_rollout_f32(cev_handle* h, int member_seat, const float* members, in
         p.status = status;
         p.n_cycles = cfg->n_cycles;
         p.pos_first = cfg->integrate_pos_first;
-        return launch_rollout_cluster(h, p, st);
+        return variant == 3 ? launch_rollout_lockstep(h, p, st) : launch_rollout_cluster(h, p, st);
     }
     GenericParams g{};
     g.w[member_seat] = members;
@@ -149,6 +161,16 @@ int cev_mpe_rollout_f32(cev_handle* h, int member_seat, const float* members, in
     g.pos_first = cfg->integrate_pos_first;
     g.N = (int64_t)P * K * E;
     return launch_rollout_generic(h, g, st);
+}
+
+int cev_mpe_rollout_plan(cev_handle* h, int P, int K, int E, int n_cycles, int variant, int* variant_used,
+                         int* n_launches) {
+    CEV_REQUIRE(h != nullptr, "mpe_rollout_plan: null handle");
+    CEV_REQUIRE(variant >= 0 && variant <= 3, "mpe_rollout_plan: variant must be 0..3");
+    const int v = rollout_plan(h, P, K, E, variant);
+    if (variant_used) *variant_used = v;
+    if (n_launches) *n_launches = v == 3 ? rollout_lockstep_launches(n_cycles) : (v == 2 ? 3 : 1);
+    return CEV_OK;
 }
 
 int cev_mpe_rollout_indexed_f32(cev_handle* h, const float* w_adv, int64_t adv_pitch, const float* w_a0,

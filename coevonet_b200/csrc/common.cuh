@@ -236,6 +236,8 @@ struct cev_handle {
     size_t workspace_bytes;
     void* opp_workspace;   // packed opponent fc2 matrices of the rollout kernel
     size_t opp_workspace_bytes;
+    void* ls_workspace;    // episode state / split opponent weights of the lockstep rollout
+    size_t ls_workspace_bytes;
 };
 
 // ---------------------------------------------------------------------------
@@ -273,6 +275,8 @@ struct ClusterParams {
 int launch_rollout_generic(cev_handle* h, const GenericParams& p, cudaStream_t stream);
 int launch_rollout_cluster(cev_handle* h, const ClusterParams& p, cudaStream_t stream);
 int rollout_cluster_max_clusters(int device);
+int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t stream);
+int rollout_lockstep_launches(int n_cycles);
 int launch_deepqn_fc_tc(cev_handle* h, const float* members, int64_t pitch, int P, int B, int n_act, int f1w_off,
                         int f1b_off, int ow_off, int ob_off, const float* act3, float* logits, int32_t* actions,
                         cudaStream_t stream);

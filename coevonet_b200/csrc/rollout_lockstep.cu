@@ -1,0 +1,944 @@
+// K1 (lockstep form): the population evaluation as one pass per world step over ALL episodes.
+//
+// Replaces, for P members x K opponent sets x E env instances (same contract as
+// rollout_cluster.cu):
+//   play_game / play_MPE          utils/game_logic_functions.py:123-228
+//   FCNetwork.forward / argmax    MPE/fcnetwork.py:37-90
+//   simple_adversary_v3 world     SURVEY.md Appendix A (third-party pettingzoo)
+//   the GA/ES evaluation loops    genetic_algorithm.py:125-217, evolutionary_strategy.py:236-251
+//
+// Why a second form: two of the three forwards of every world step use the OPPONENTS'
+// weights, which are shared by every episode of the launch (the ES base agents,
+// evolutionary_strategy.py:77/94/111; the GA Hall-of-Fame rows, genetic_algorithm.py:138-139).
+// With all episodes advanced in lockstep that work is a dense [episodes x 512] . [512 x 256]
+// GEMM and belongs on the tensor cores; only the member's own forward (unique weights per
+// member) stays on the FP32 pipe.  Per world step:
+//
+//   ls_member_kernel  one CTA per (member, 16 episodes): layer 1 + LayerNorm on CUDA cores, fc2 with
+//                     packed FFMA2 from 8 KB TMA tensor tiles ([64 rows x 32 k], 128B swizzle) of the
+//                     member's own row streamed from HBM/L2 (16 slots, each warp double-buffers its
+//                     own tiles, no CTA-wide barrier in the loop), LayerNorm-2 + output layer +
+//                     first-max argmax inside the CTA (no cluster, no DSMEM).
+//   ls_opp_kernel     persistent, one CTA per SM, job = (opponent seat, opponent set, 128 episodes):
+//                     8 producer warps compute layer 1 + LayerNorm + ReLU for their episode rows and
+//                     write the activations, split into TF32 hi + lo parts, straight into the
+//                     128B-swizzled K-major A tiles; one thread streams the pre-split opponent fc2
+//                     matrix with TMA; one thread issues tcgen05.mma kind::tf32 (M=128, N=256, K=8)
+//                     three times per k-step (hi.hi + lo.hi + hi.lo = "3xTF32", fp32-level accuracy)
+//                     into a double-buffered TMEM accumulator; 4 epilogue warps read it back with
+//                     tcgen05.ld and do bias + LayerNorm-2 + ReLU + output layer + argmax per row.
+//                     Layer-1 LayerNorm statistics come from the closed form mean = wbar.x + bbar,
+//                     var = z^T C z (z = [x; 1], C = row covariance of [W1 | b1], fp64), so a
+//                     producer never needs the whole 512-vector at once.
+//   ls_env_step_kernel one thread per episode: fp64 physics, rewards, next observations
+//                     (bit-exact with oracle/mpe_env.py given equal actions).
+//
+// Arithmetic: member forward fp32 (FFMA); opponent fc2 3xTF32 with fp32 accumulation (error
+// ~1e-6 of the activations' scale, the same order as fp32 summation-order noise); environment fp64.
+#include "rollout_common.cuh"
+#include "tc_common.cuh"
+
+namespace cev {
+
+// ---------------------------------------------------------------------------------------------
+// workspace layout
+// ---------------------------------------------------------------------------------------------
+constexpr int LS_ST_FIELDS = 16;       // px[3] py[3] vx[3] vy[3] lx[2] ly[2]
+constexpr int LS_OBS_PAD = 12;         // floats per (seat, episode) observation record
+constexpr int LS_L1S = 132;            // doubles per opponent row: wbar[11] | C[11][11]
+
+struct LsBuffers {
+    double* st;        // [16][N]
+    double* acc;       // [3][N]  sum_good, last_good, sum_adv
+    float* min_gap;    // [N]
+    int32_t* goal;     // [N]
+    float* obs;        // [3][N][12]
+    int32_t* act;      // [3][N]
+    float* gap;        // [3][N]
+    float* w2split;    // [2 seats][K][hi, lo][256][512]
+    double* l1stats;   // [2 seats][K][132]
+};
+
+static size_t ls_align(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static size_t ls_carve(void* base, int64_t N, int K, LsBuffers* b) {
+    size_t off = 0;
+    char* p = static_cast<char*>(base);
+    auto take = [&](size_t bytes) {
+        void* r = p ? p + off : nullptr;
+        off += ls_align(bytes);
+        return r;
+    };
+    LsBuffers t;
+    t.w2split = static_cast<float*>(take((size_t)2 * K * 2 * H2 * H1 * sizeof(float)));
+    t.st = static_cast<double*>(take((size_t)LS_ST_FIELDS * N * sizeof(double)));
+    t.acc = static_cast<double*>(take((size_t)3 * N * sizeof(double)));
+    t.min_gap = static_cast<float*>(take((size_t)N * sizeof(float)));
+    t.goal = static_cast<int32_t*>(take((size_t)N * sizeof(int32_t)));
+    t.obs = static_cast<float*>(take((size_t)3 * N * LS_OBS_PAD * sizeof(float)));
+    t.act = static_cast<int32_t*>(take((size_t)3 * N * sizeof(int32_t)));
+    t.gap = static_cast<float*>(take((size_t)3 * N * sizeof(float)));
+    t.l1stats = static_cast<double*>(take((size_t)2 * K * LS_L1S * sizeof(double)));
+    if (b) *b = t;
+    return off;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-episode state helpers (SoA in the workspace)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ls_store_state(const LsBuffers& b, int64_t N, int64_t ep, const EnvState& s) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        b.st[(0 + i) * N + ep] = s.px[i];
+        b.st[(3 + i) * N + ep] = s.py[i];
+        b.st[(6 + i) * N + ep] = s.vx[i];
+        b.st[(9 + i) * N + ep] = s.vy[i];
+    }
+#pragma unroll
+    for (int l = 0; l < 2; ++l) {
+        b.st[(12 + l) * N + ep] = s.lx[l];
+        b.st[(14 + l) * N + ep] = s.ly[l];
+    }
+}
+__device__ __forceinline__ void ls_load_state(const LsBuffers& b, int64_t N, int64_t ep, EnvState& s) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        s.px[i] = b.st[(0 + i) * N + ep];
+        s.py[i] = b.st[(3 + i) * N + ep];
+        s.vx[i] = b.st[(6 + i) * N + ep];
+        s.vy[i] = b.st[(9 + i) * N + ep];
+    }
+#pragma unroll
+    for (int l = 0; l < 2; ++l) {
+        s.lx[l] = b.st[(12 + l) * N + ep];
+        s.ly[l] = b.st[(14 + l) * N + ep];
+    }
+    s.goal = b.goal[ep];
+}
+__device__ __forceinline__ void ls_store_obs(const LsBuffers& b, int64_t N, int64_t ep, const EnvState& s) {
+#pragma unroll
+    for (int seat = 0; seat < 3; ++seat) {
+        float o[LS_OBS_PAD];
+#pragma unroll
+        for (int j = 0; j < LS_OBS_PAD; ++j) o[j] = 0.f;
+        env_observe(s, seat, o);
+        float4* dst = reinterpret_cast<float4*>(b.obs + ((int64_t)seat * N + ep) * LS_OBS_PAD);
+        dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+        dst[2] = make_float4(o[8], o[9], o[10], o[11]);
+    }
+}
+
+struct LsEnvParams {
+    LsBuffers b;
+    int64_t N;
+    int K, E, init_shared, pos_first, last;
+    const double* init;
+    double* out;
+};
+
+__global__ void __launch_bounds__(256) ls_init_kernel(const LsEnvParams p) {
+    const int64_t ep = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ep >= p.N) return;
+    const int e = (int)(ep % p.E), k = (int)((ep / p.E) % p.K);
+    const int64_t rec = p.init_shared ? ((int64_t)k * p.E + e) : ep;
+    EnvState s;
+    env_load(s, p.init + rec * CEV_INIT_STATE_DIM);
+    ls_store_state(p.b, p.N, ep, s);
+    p.b.goal[ep] = s.goal;
+    p.b.acc[ep] = 0.0;
+    p.b.acc[p.N + ep] = 0.0;
+    p.b.acc[2 * p.N + ep] = 0.0;
+    p.b.min_gap[ep] = CUDART_INF_F;
+    ls_store_obs(p.b, p.N, ep, s);
+    if (p.last) {   // n_cycles == 0: nothing is played
+        double* o = p.out + ep * CEV_ROLLOUT_OUT_DIM;
+        o[0] = 0.0;
+        o[1] = 0.0;
+        o[2] = 0.0;
+        o[3] = (double)CUDART_INF_F;
+    }
+}
+
+__global__ void __launch_bounds__(256) ls_env_step_kernel(const LsEnvParams p) {
+    const int64_t ep = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ep >= p.N) return;
+    EnvState s;
+    ls_load_state(p.b, p.N, ep, s);
+    const int act[3] = {p.b.act[ep], p.b.act[p.N + ep], p.b.act[2 * p.N + ep]};
+    const float g = fminf(p.b.gap[ep], fminf(p.b.gap[p.N + ep], p.b.gap[2 * p.N + ep]));
+    double rg, ra;
+    env_step(s, act, p.pos_first != 0, rg, ra);
+    const double sum_good = __dadd_rn(p.b.acc[ep], rg);
+    const double sum_adv = __dadd_rn(p.b.acc[2 * p.N + ep], ra);
+    const float min_gap = fminf(p.b.min_gap[ep], g);
+    if (p.last) {
+        double* o = p.out + ep * CEV_ROLLOUT_OUT_DIM;
+        o[0] = sum_good;
+        o[1] = rg;
+        o[2] = sum_adv;
+        o[3] = (double)min_gap;
+        return;
+    }
+    p.b.acc[ep] = sum_good;
+    p.b.acc[p.N + ep] = rg;
+    p.b.acc[2 * p.N + ep] = sum_adv;
+    p.b.min_gap[ep] = min_gap;
+    ls_store_state(p.b, p.N, ep, s);
+    ls_store_obs(p.b, p.N, ep, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// opponent preparation (once per launch): TF32 hi/lo split of fc2.W, layer-1 row statistics
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+struct LsPrepParams {
+    const float* opp[2];
+    int64_t opp_pitch[2];
+    int seat[2];
+    int K;
+    float* w2split;
+    double* l1stats;
+};
+
+__global__ void __launch_bounds__(256) ls_split_w2_kernel(const LsPrepParams p) {
+    const int oi = blockIdx.y / p.K, k = blockIdx.y % p.K;
+    const FcOffsets o = fc_offsets(seat_in_dim(p.seat[oi]));
+    const float4* src = reinterpret_cast<const float4*>(p.opp[oi] + (int64_t)k * p.opp_pitch[oi] + o.fc2w);
+    float4* hi = reinterpret_cast<float4*>(p.w2split + (size_t)(blockIdx.y * 2 + 0) * H2 * H1);
+    float4* lo = reinterpret_cast<float4*>(p.w2split + (size_t)(blockIdx.y * 2 + 1) * H2 * H1);
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < H2 * H1 / 4; f += gridDim.x * blockDim.x) {
+        const float4 w = src[f];
+        float4 h, l;
+        h.x = tf32_rna(w.x); l.x = tf32_rna(w.x - h.x);
+        h.y = tf32_rna(w.y); l.y = tf32_rna(w.y - h.y);
+        h.z = tf32_rna(w.z); l.z = tf32_rna(w.z - h.z);
+        h.w = tf32_rna(w.w); l.w = tf32_rna(w.w - h.w);
+        hi[f] = h;
+        lo[f] = l;
+    }
+}
+
+// wbar[j] = mean over the 512 rows of column j of [W1 | b1]; C[a][b] = row covariance (biased).
+// LayerNorm-1 of y = W1 x + b1:  mean(y) = wbar . z,  var(y) = z^T C z  with z = [x; 1]
+// (MPE/fcnetwork.py:44: nn.LayerNorm(512), biased variance).
+__global__ void __launch_bounds__(128) ls_l1stats_kernel(const LsPrepParams p) {
+    const int oi = blockIdx.x / p.K, k = blockIdx.x % p.K;
+    const int in = seat_in_dim(p.seat[oi]), d = in + 1;
+    const float* row = p.opp[oi] + (int64_t)k * p.opp_pitch[oi];
+    const float* w1 = row;
+    const float* b1 = row + H1 * in;
+    __shared__ double wbar[11];
+    const int t = threadIdx.x;
+    if (t < 11) {
+        double s = 0.0;
+        if (t < d)
+            for (int r = 0; r < H1; ++r) s += (double)(t < in ? w1[r * in + t] : b1[r]);
+        wbar[t] = s / H1;
+    }
+    __syncthreads();
+    double* out = p.l1stats + (size_t)blockIdx.x * LS_L1S;
+    if (t < 11) out[t] = wbar[t];
+    if (t < 121) {
+        const int a = t / 11, b = t % 11;
+        double s = 0.0;
+        if (a < d && b < d)
+            for (int r = 0; r < H1; ++r) {
+                const double va = (double)(a < in ? w1[r * in + a] : b1[r]) - wbar[a];
+                const double vb = (double)(b < in ? w1[r * in + b] : b1[r]) - wbar[b];
+                s += va * vb;
+            }
+        out[11 + t] = s / H1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// member forward (FP32 pipe)
+// ---------------------------------------------------------------------------------------------
+constexpr int LS_BT = 16;                         // episodes per CTA
+constexpr int LS_TILE_BYTES = 64 * 32 * 4;        // [64 rows x 32 k] fp32
+constexpr int LS_NSLOT = 16;
+constexpr int LS_NTILE = 64;                      // 4 row quarters x 16 k-tiles per member
+constexpr int LS_TAIL_FLOATS = 2056;              // fc2.b | ln2.g | ln2.b | out.W | out.b (+3 pad), contiguous in the row
+constexpr int LS_W1A_FLOATS = H1 * IN_GOOD + 3 * H1;
+
+struct LsMemberSmem {
+    static constexpr size_t off_ring = 0;
+    static constexpr size_t off_h1p = off_ring + (size_t)LS_NSLOT * LS_TILE_BYTES;
+    static constexpr size_t off_w1a = off_h1p + (size_t)H1 * LS_BT * 4;
+    static constexpr size_t off_tail = off_w1a + (size_t)LS_W1A_FLOATS * 4;
+    static constexpr size_t off_obs = off_tail + (size_t)LS_TAIL_FLOATS * 4;
+    static constexpr size_t off_red1 = off_obs + (size_t)LS_BT * 12 * 4;
+    static constexpr size_t off_red = off_red1 + (size_t)2 * NW * LS_BT * 4;
+    static constexpr size_t off_flag = off_red + (size_t)7 * NW * LS_BT * 4;
+    static constexpr size_t off_bar = off_flag + 16;
+    static constexpr size_t total = off_bar + (size_t)(LS_NSLOT + 2) * 8 + 1024 /*alignment slack*/;
+};
+
+struct LsMemberParams {
+    const float* members;
+    int64_t pitch;
+    int n_chunks, KE, seat;
+    int64_t N;
+    const float* obs;     // this seat's [N][12]
+    int32_t* act;         // this seat's [N]
+    float* gap;
+    int32_t* status;
+};
+
+// One [64 rows x 32 k] tile of fc2 for one warp: lane = (eg = lane % 4: 4 envs, rl = lane / 4: row lane),
+// rows rl + 8 i (i < 8).  Tile rows are 128 bytes, 16-byte chunk c of row r stored at c ^ (r & 7)
+// (TMA SWIZZLE_128B): the 8 row lanes of a load hit 8 distinct bank groups.
+__device__ __forceinline__ void ls_fc2_tile(const float4* __restrict__ tile, const float* __restrict__ h1p, int kbase,
+                                            float2 (&acc)[8][4]) {
+    const int lane = threadIdx.x & 31;
+    const int eg = lane & 3, rl = lane >> 2;
+    const float4* wrow0 = tile + rl * 8;
+    const float* hbase = h1p + (kbase >> 1) * (2 * LS_BT) + eg * 8;
+#pragma unroll
+    for (int st = 0; st < 8; ++st) {
+        float4 a[2][2];
+#pragma unroll
+        for (int kp = 0; kp < 2; ++kp)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                a[kp][j] = *reinterpret_cast<const float4*>(hbase + (2 * st + kp) * (2 * LS_BT) + j * 4);
+        const int col = st ^ rl;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 w = wrow0[i * 64 + col];
+            const float2 w0 = make_float2(w.x, w.y), w1 = make_float2(w.z, w.w);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                acc[i][2 * j] = ffma2(w0, make_float2(a[0][j].x, a[0][j].y), acc[i][2 * j]);
+                acc[i][2 * j] = ffma2(w1, make_float2(a[1][j].x, a[1][j].y), acc[i][2 * j]);
+                acc[i][2 * j + 1] = ffma2(w0, make_float2(a[0][j].z, a[0][j].w), acc[i][2 * j + 1]);
+                acc[i][2 * j + 1] = ffma2(w1, make_float2(a[1][j].z, a[1][j].w), acc[i][2 * j + 1]);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(CT, 1)
+ls_member_kernel(const __grid_constant__ CUtensorMap map_w2, const LsMemberParams p) {
+    using L = LsMemberSmem;
+    constexpr int BT = LS_BT;
+    constexpr int G = CT / BT;       // 16 row groups
+    constexpr int RP = H2 / G;       // 16 fc2 rows per thread after the k-split reduce
+    extern __shared__ unsigned char ls_raw[];
+    unsigned char* smem =
+        reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ls_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* ring = smem + L::off_ring;
+    float* h1p = reinterpret_cast<float*>(smem + L::off_h1p);        // activations, later the k-split partials
+    float* w1a = reinterpret_cast<float*>(smem + L::off_w1a);
+    float* tail = reinterpret_cast<float*>(smem + L::off_tail);
+    float* obs = reinterpret_cast<float*>(smem + L::off_obs);
+    float* red1 = reinterpret_cast<float*>(smem + L::off_red1);
+    float* redA = reinterpret_cast<float*>(smem + L::off_red);       // [NW][BT]
+    float* redB = redA + NW * BT;                                    // [NW][BT]
+    float* redC = redB + NW * BT;                                    // [NW][5][BT]
+    int* flag = reinterpret_cast<int*>(smem + L::off_flag);
+    uint64_t* bar_tile = reinterpret_cast<uint64_t*>(smem + L::off_bar);   // [LS_NSLOT]
+    uint64_t* bar_w1 = bar_tile + LS_NSLOT;
+    uint64_t* bar_tail = bar_w1 + 1;
+
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int m = blockIdx.x / p.n_chunks, ch = blockIdx.x % p.n_chunks;
+    const int n_env = min(BT, p.KE - ch * BT);
+    const int64_t ep0 = (int64_t)m * p.KE + (int64_t)ch * BT;
+    const float* mrow = p.members + (int64_t)m * p.pitch;
+    const int in_dim = seat_in_dim(p.seat);
+    const FcOffsets om = fc_offsets(in_dim);
+
+    if (t == 0) {
+        *flag = 0;
+        for (int i = 0; i < LS_NSLOT + 2; ++i) mbar_init(bar_tile + i, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    // tile sequence s = i * 8 + w: the i-th tile of warp w = row quarter (w & 3), k-tile (w >> 2) * 8 + i;
+    // it lives in slot s % 16, so warp w double-buffers its own stream in slots w and w + 8.
+    auto issue_tile = [&](int s) {
+        const int w = s & 7, i = s >> 3, slot = s & (LS_NSLOT - 1);
+        const int kt = (w >> 2) * 8 + i, rq = w & 3;
+        mbar_arrive_expect_tx(bar_tile + slot, LS_TILE_BYTES);
+        tma_load_3d(ring + (size_t)slot * LS_TILE_BYTES, &map_w2, bar_tile + slot, kt * 32, rq * 64, m);
+    };
+    if (t == 0) {
+        const uint32_t w1_bytes = (uint32_t)(H1 * in_dim + 3 * H1) * 4;
+        mbar_arrive_expect_tx(bar_w1, w1_bytes);
+        bulk_g2s(w1a, mrow, w1_bytes, bar_w1);
+#pragma unroll 1
+        for (int s = 0; s < LS_NSLOT; ++s) issue_tile(s);
+        mbar_arrive_expect_tx(bar_tail, LS_TAIL_FLOATS * 4);
+        bulk_g2s(tail, mrow + om.fc2b, LS_TAIL_FLOATS * 4, bar_tail);
+    }
+    if (t < BT * 3) {
+        const int e = t / 3, v = t % 3;
+        const int64_t ep = ep0 + (e < n_env ? e : 0);
+        reinterpret_cast<float4*>(obs)[e * 3 + v] = __ldg(reinterpret_cast<const float4*>(p.obs) + ep * 3 + v);
+    }
+    __syncthreads();
+    mbar_wait(bar_w1, 0);
+    if (p.seat == 0) layer1<BT, IN_ADV>(w1a, obs, h1p, red1, flag);
+    else layer1<BT, IN_GOOD>(w1a, obs, h1p, red1, flag);
+    __syncthreads();
+
+    // ---- fc2: warp w = (row quarter w & 3, k half w >> 2), 8 tiles of [64 x 32] ----------------
+    float2 acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
+#pragma unroll 1
+    for (int i = 0; i < 8; ++i) {
+        const int slot = warp + 8 * (i & 1);
+        mbar_wait(bar_tile + slot, (uint32_t)(i >> 1));
+        ls_fc2_tile(reinterpret_cast<const float4*>(ring + (size_t)slot * LS_TILE_BYTES), h1p,
+                    ((warp >> 2) * 8 + i) * 32, acc);
+        __syncwarp();
+        if (lane == 0 && i + 2 < 8) issue_tile((i + 2) * 8 + warp);
+    }
+    __syncthreads();          // every warp is done reading h1p
+    {
+        float* part = h1p;    // [2 k-halves][256 rows][BT]
+        const int eg = lane & 3, rl = lane >> 2;
+        const int kh = warp >> 2, rq = warp & 3;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int row = rq * 64 + rl + 8 * i;
+            float4 v;
+            v.x = acc[i][0].x + acc[i][0].y;
+            v.y = acc[i][1].x + acc[i][1].y;
+            v.z = acc[i][2].x + acc[i][2].y;
+            v.w = acc[i][3].x + acc[i][3].y;
+            *reinterpret_cast<float4*>(part + ((size_t)(kh * H2 + row)) * BT + eg * 4) = v;
+        }
+    }
+    __syncthreads();
+    mbar_wait(bar_tail, 0);
+    const float* b2 = tail;
+    const float* g2 = tail + H2;
+    const float* be2 = tail + 2 * H2;
+    const float* w3 = tail + 3 * H2;
+    const float* b3 = tail + 3 * H2 + NACT * H2;
+    const int e1 = t % BT, g1 = t / BT;
+    float pre2[RP];
+    float lsum = 0.f;
+#pragma unroll
+    for (int j = 0; j < RP; ++j) {
+        const int row = g1 + G * j;
+        pre2[j] = (h1p[(size_t)row * BT + e1] + h1p[(size_t)(H2 + row) * BT + e1]) + b2[row];
+        lsum += pre2[j];
+    }
+    lsum = group_sum<BT>(lsum);
+    if (lane < BT) redA[warp * BT + e1] = lsum;
+    __syncthreads();
+    float mean = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) mean += redA[w * BT + e1];
+    mean *= (1.0f / H2);
+    float lsq = 0.f;
+#pragma unroll
+    for (int j = 0; j < RP; ++j) {
+        const float d = pre2[j] - mean;
+        lsq = fmaf(d, d, lsq);
+    }
+    lsq = group_sum<BT>(lsq);
+    if (lane < BT) redB[warp * BT + e1] = lsq;
+    __syncthreads();
+    float var = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) var += redB[w * BT + e1];
+    var *= (1.0f / H2);
+    if (!isfinite(mean) || !isfinite(var)) *flag = 1;
+    const float rstd = 1.0f / sqrtf(var + LN_EPS);
+    float pl[NACT] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < RP; ++j) {
+        const int row = g1 + G * j;
+        const float h = fmaxf(fmaf((pre2[j] - mean) * rstd, g2[row], be2[row]), 0.f);
+#pragma unroll
+        for (int a = 0; a < NACT; ++a) pl[a] = fmaf(w3[a * H2 + row], h, pl[a]);
+    }
+#pragma unroll
+    for (int a = 0; a < NACT; ++a) {
+        const float v = group_sum<BT>(pl[a]);
+        if (lane < BT) redC[(warp * NACT + a) * BT + e1] = v;
+    }
+    __syncthreads();
+    if (t < BT) {
+        float lg[NACT];
+        bool fin = true;
+#pragma unroll
+        for (int a = 0; a < NACT; ++a) {
+            float v = redC[a * BT + t];
+#pragma unroll
+            for (int w = 1; w < NW; ++w) v += redC[(w * NACT + a) * BT + t];
+            lg[a] = v + b3[a];
+            fin = fin && isfinite(lg[a]);
+        }
+        if (!fin) *flag = 1;
+        float gap;
+        const int a = argmax_first5(lg, gap);
+        if (t < n_env) {
+            p.act[ep0 + t] = a;
+            p.gap[ep0 + t] = gap;
+        }
+    }
+    __syncthreads();
+    if (t == 0 && *flag && p.status) atomicOr(p.status, CEV_STATUS_NONFINITE);
+}
+
+// ---------------------------------------------------------------------------------------------
+// opponent forward (tcgen05, 3xTF32)
+// ---------------------------------------------------------------------------------------------
+constexpr int OP_THREADS = 448;                   // warps 0-3 epilogue, 4-11 A producers, 12 TMA, 13 MMA
+constexpr int OP_PROD = 256;
+constexpr int OP_BM = 128, OP_BN = 256, OP_BK = 32, OP_KT = H1 / OP_BK;
+constexpr uint32_t OP_A_BYTES = OP_BM * OP_BK * 4;          // 16 KB
+constexpr uint32_t OP_B_BYTES = OP_BN * OP_BK * 4;          // 32 KB
+constexpr uint32_t OP_STAGE_BYTES = 2 * OP_A_BYTES + 2 * OP_B_BYTES;   // A hi | A lo | B hi | B lo = 96 KB
+constexpr int OP_STAGES = 2;
+constexpr size_t OP_OFF_W1A = (size_t)OP_STAGES * OP_STAGE_BYTES;
+constexpr size_t OP_OFF_BAR = OP_OFF_W1A + (size_t)LS_W1A_FLOATS * 4;
+constexpr size_t OP_SMEM = OP_OFF_BAR + 256 + 1024 /*alignment slack*/;
+constexpr uint32_t OP_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(OP_BN >> 3) << 17) |
+                              ((uint32_t)(OP_BM >> 4) << 24);
+
+struct LsOppParams {
+    const float* opp[2];
+    int64_t opp_pitch[2];
+    int seat[2];
+    int K, E, n_tiles, n_jobs;
+    int64_t PE;              // P * E rows per (seat, k)
+    int64_t N;
+    const float* obs;        // [3][N][12]
+    int32_t* act;            // [3][N]
+    float* gap;
+    const double* l1stats;
+    int32_t* status;
+};
+
+__device__ __forceinline__ void op_umma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(OP_IDESC), "r"(accumulate)
+        : "memory");
+}
+
+// One producer thread's share of an A tile: 16 of the 32 activations of k-tile kt for episode row r
+// (4 of the 8 16-byte chunks), relu(LN1(W1 x + b1)), split into TF32 hi + lo and stored K-major with
+// the 128-byte swizzle the UMMA descriptor expects (chunk c of row r at c ^ (r & 7)).
+template <int IN>
+__device__ __forceinline__ void op_produce_half(const float* __restrict__ w1a, const float (&x)[LS_OBS_PAD], float mean,
+                                                float rstd, int kt, int half, int r, unsigned char* a_hi,
+                                                unsigned char* a_lo) {
+    const float* fc1b = w1a + H1 * IN;
+    const float* ln1g = fc1b + H1;
+    const float* ln1b = ln1g + H1;
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        const int c = half * 4 + cc;
+        const int k0 = kt * OP_BK + c * 4;
+        const float4 bb = *reinterpret_cast<const float4*>(fc1b + k0);
+        const float4 gg = *reinterpret_cast<const float4*>(ln1g + k0);
+        const float4 ee = *reinterpret_cast<const float4*>(ln1b + k0);
+        const float bq[4] = {bb.x, bb.y, bb.z, bb.w}, gq[4] = {gg.x, gg.y, gg.z, gg.w}, eq[4] = {ee.x, ee.y, ee.z, ee.w};
+        float hi[4], lo[4];
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+            const float2* wr = reinterpret_cast<const float2*>(w1a + (k0 + qq) * IN);
+            float pre = 0.f;
+#pragma unroll
+            for (int i2 = 0; i2 < IN / 2; ++i2) {
+                const float2 w = wr[i2];
+                pre = fmaf(w.x, x[2 * i2], pre);
+                pre = fmaf(w.y, x[2 * i2 + 1], pre);
+            }
+            pre += bq[qq];
+            const float h = fmaxf(fmaf((pre - mean) * rstd, gq[qq], eq[qq]), 0.f);
+            hi[qq] = tf32_rna(h);
+            lo[qq] = tf32_rna(h - hi[qq]);
+        }
+        const int off = (c ^ (r & 7)) << 4;
+        *reinterpret_cast<float4*>(a_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(a_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+__global__ void __launch_bounds__(OP_THREADS, 1)
+ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
+    extern __shared__ unsigned char op_raw[];
+    unsigned char* base =
+        reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(op_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* stage_mem = base;
+    float* w1a = reinterpret_cast<float*>(base + OP_OFF_W1A);
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(base + OP_OFF_BAR);   // [2] A written + B landed
+    uint64_t* bar_empty = bar_full + OP_STAGES;                             // [2] MMAs retired
+    uint64_t* bar_tfull = bar_empty + OP_STAGES;                            // [2] accumulator ready
+    uint64_t* bar_tempty = bar_tfull + 2;                                   // [2] accumulator drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+    int* flag = reinterpret_cast<int*>(tmem_slot + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        *flag = 0;
+        for (int i = 0; i < OP_STAGES; ++i) {
+            tc_mbar_init(bar_full + i, OP_PROD + 1);
+            tc_mbar_init(bar_empty + i, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            tc_mbar_init(bar_tfull + i, 1);
+            tc_mbar_init(bar_tempty + i, 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 13) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tc_smem_u32(tmem_slot)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const int jobs_per_ok = p.n_tiles;
+
+    if (warp < 4) {
+        // ===================== epilogue: bias + LayerNorm-2 + ReLU + output layer + argmax =====
+        const int q = warp;
+        uint32_t pass = 0;
+        for (int job = blockIdx.x; job < p.n_jobs; job += gridDim.x, ++pass) {
+            const int okey = job / jobs_per_ok, tile = job % jobs_per_ok;
+            const int oi = okey / p.K, k = okey % p.K;
+            const int seat = p.seat[oi];
+            const FcOffsets o = fc_offsets(seat_in_dim(seat));
+            const float* row = p.opp[oi] + (int64_t)k * p.opp_pitch[oi];
+            const float* b2 = row + o.fc2b;
+            const float* g2 = row + o.ln2g;
+            const float* be2 = row + o.ln2b;
+            const float* w3 = row + o.outw;
+            const float* b3 = row + o.outb;
+            const int64_t j = (int64_t)tile * OP_BM + q * 32 + lane;
+            const bool valid = j < p.PE;
+            const int64_t jj = valid ? j : p.PE - 1;
+            const int64_t ep = ((jj / p.E) * p.K + k) * p.E + (jj % p.E);
+            const uint32_t as = pass & 1, ause = pass >> 1;
+            tc_mbar_wait(bar_tfull + as, ause & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * OP_BN;
+            float sum = 0.f;
+#pragma unroll 1
+            for (int c0 = 0; c0 < OP_BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c0, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) sum += __uint_as_float(v[i]) + __ldg(b2 + c0 + i);
+            }
+            const float mean = sum * (1.0f / H2);
+            float sq = 0.f;
+#pragma unroll 1
+            for (int c0 = 0; c0 < OP_BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c0, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float d = (__uint_as_float(v[i]) + __ldg(b2 + c0 + i)) - mean;
+                    sq = fmaf(d, d, sq);
+                }
+            }
+            const float var = sq * (1.0f / H2);
+            const float rstd = 1.0f / sqrtf(var + LN_EPS);
+            float lg[NACT] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+            for (int c0 = 0; c0 < OP_BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c0, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int c = c0 + i;
+                    const float x = (__uint_as_float(v[i]) + __ldg(b2 + c)) - mean;
+                    const float h = fmaxf(fmaf(x * rstd, __ldg(g2 + c), __ldg(be2 + c)), 0.f);
+#pragma unroll
+                    for (int a = 0; a < NACT; ++a) lg[a] = fmaf(__ldg(w3 + a * H2 + c), h, lg[a]);
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            __syncwarp();
+            if (lane == 0) tc_mbar_arrive(bar_tempty + as);
+            bool fin = isfinite(mean) && isfinite(var);
+#pragma unroll
+            for (int a = 0; a < NACT; ++a) {
+                lg[a] += __ldg(b3 + a);
+                fin = fin && isfinite(lg[a]);
+            }
+            float gap;
+            const int a = argmax_first5(lg, gap);
+            if (valid) {
+                if (!fin) *flag = 1;
+                p.act[(int64_t)seat * p.N + ep] = a;
+                p.gap[(int64_t)seat * p.N + ep] = gap;
+            }
+        }
+    } else if (warp < 12) {
+        // ===================== A producers: layer 1 + LayerNorm + ReLU -> TF32 hi/lo tiles =====
+        const int pt = threadIdx.x - 128;
+        const int r = pt & 127, half = pt >> 7;       // episode row, which 4 of the 8 16-byte chunks
+        int cur_ok = -1;
+        uint32_t it = 0;
+        for (int job = blockIdx.x; job < p.n_jobs; job += gridDim.x) {
+            const int okey = job / jobs_per_ok, tile = job % jobs_per_ok;
+            const int oi = okey / p.K, k = okey % p.K;
+            const int seat = p.seat[oi];
+            const int in = seat_in_dim(seat);
+            const float* row = p.opp[oi] + (int64_t)k * p.opp_pitch[oi];
+            if (okey != cur_ok) {
+                asm volatile("bar.sync 1, 256;\n" ::: "memory");       // producers done with the old block
+                const int n4 = (H1 * in + 3 * H1) / 4;
+                for (int f = pt; f < n4; f += OP_PROD)
+                    reinterpret_cast<float4*>(w1a)[f] = __ldg(reinterpret_cast<const float4*>(row) + f);
+                asm volatile("bar.sync 1, 256;\n" ::: "memory");
+                cur_ok = okey;
+            }
+            const int64_t j = (int64_t)tile * OP_BM + r;
+            const int64_t jj = j < p.PE ? j : p.PE - 1;
+            const int64_t ep = ((jj / p.E) * p.K + k) * p.E + (jj % p.E);
+            float x[LS_OBS_PAD];
+            {
+                const float4* src = reinterpret_cast<const float4*>(p.obs + ((int64_t)seat * p.N + ep) * LS_OBS_PAD);
+                const float4 v0 = __ldg(src), v1 = __ldg(src + 1), v2 = __ldg(src + 2);
+                x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
+                x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+                x[8] = v2.x; x[9] = v2.y; x[10] = v2.z; x[11] = v2.w;
+            }
+            // LayerNorm-1 statistics in closed form (fp64): mean = wbar . z, var = z^T C z, z = [x; 1]
+            float mean, rstd;
+            {
+                const double* S = p.l1stats + (size_t)okey * LS_L1S;
+                double z[11];
+#pragma unroll
+                for (int a = 0; a < 11; ++a) z[a] = a < in ? (double)x[a] : (a == in ? 1.0 : 0.0);
+                double md = 0.0, vd = 0.0;
+#pragma unroll
+                for (int a = 0; a < 11; ++a) {
+                    md = fma(__ldg(S + a), z[a], md);
+                    double ra = 0.0;
+#pragma unroll
+                    for (int b = 0; b < 11; ++b) ra = fma(__ldg(S + 11 + a * 11 + b), z[b], ra);
+                    vd = fma(ra, z[a], vd);
+                }
+                mean = (float)md;
+                const float var = (float)vd;
+                if (!isfinite(mean) || !isfinite(var)) *flag = 1;
+                rstd = 1.0f / sqrtf(var + LN_EPS);
+            }
+            for (int kt = 0; kt < OP_KT; ++kt, ++it) {
+                const uint32_t st = it % OP_STAGES, use = it / OP_STAGES;
+                if (use > 0) tc_mbar_wait(bar_empty + st, (use - 1) & 1);
+                unsigned char* a_hi = stage_mem + (size_t)st * OP_STAGE_BYTES + (size_t)r * 128;
+                unsigned char* a_lo = a_hi + OP_A_BYTES;
+                if (in == IN_GOOD) op_produce_half<IN_GOOD>(w1a, x, mean, rstd, kt, half, r, a_hi, a_lo);
+                else op_produce_half<IN_ADV>(w1a, x, mean, rstd, kt, half, r, a_hi, a_lo);
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic writes -> tensor core reads
+                tc_mbar_arrive(bar_full + st);
+            }
+        }
+    } else if (warp == 12) {
+        // ===================== TMA: pre-split opponent fc2 (hi | lo), [256 x 32] boxes ==========
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int job = blockIdx.x; job < p.n_jobs; job += gridDim.x) {
+                const int okey = job / jobs_per_ok;
+                for (int kt = 0; kt < OP_KT; ++kt, ++it) {
+                    const uint32_t st = it % OP_STAGES, use = it / OP_STAGES;
+                    if (use > 0) tc_mbar_wait(bar_empty + st, (use - 1) & 1);
+                    unsigned char* b_hi = stage_mem + (size_t)st * OP_STAGE_BYTES + 2 * OP_A_BYTES;
+                    tc_mbar_expect_tx(bar_full + st, 2 * OP_B_BYTES);
+                    tma_load_2d(b_hi, &map_b, bar_full + st, kt * OP_BK, (okey * 2 + 0) * H2);
+                    tma_load_2d(b_hi + OP_B_BYTES, &map_b, bar_full + st, kt * OP_BK, (okey * 2 + 1) * H2);
+                }
+            }
+        }
+    } else {
+        // ===================== MMA issuer =====================
+        uint32_t it = 0, pass = 0;
+        for (int job = blockIdx.x; job < p.n_jobs; job += gridDim.x, ++pass) {
+            const uint32_t as = pass & 1, ause = pass >> 1;
+            if (ause > 0) tc_mbar_wait(bar_tempty + as, (ause - 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const uint32_t d_tmem = tmem_base + as * OP_BN;
+            for (int kt = 0; kt < OP_KT; ++kt, ++it) {
+                const uint32_t st = it % OP_STAGES, use = it / OP_STAGES;
+                tc_mbar_wait(bar_full + st, use & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                if (lane == 0) {
+                    const uint32_t s_addr = tc_smem_u32(stage_mem + (size_t)st * OP_STAGE_BYTES);
+                    const uint64_t a_hi = umma_desc_sw128(s_addr);
+                    const uint64_t a_lo = umma_desc_sw128(s_addr + OP_A_BYTES);
+                    const uint64_t b_hi = umma_desc_sw128(s_addr + 2 * OP_A_BYTES);
+                    const uint64_t b_lo = umma_desc_sw128(s_addr + 2 * OP_A_BYTES + OP_B_BYTES);
+#pragma unroll
+                    for (int k8 = 0; k8 < OP_BK / 8; ++k8) {
+                        const uint64_t ko = (uint64_t)(k8 * 2);           // 8 tf32 = 32 bytes
+                        op_umma(d_tmem, a_lo + ko, b_hi + ko, (kt | k8) ? 1u : 0u);   // small terms first
+                        op_umma(d_tmem, a_hi + ko, b_lo + ko, 1u);
+                        op_umma(d_tmem, a_hi + ko, b_hi + ko, 1u);
+                    }
+                    umma_commit(bar_empty + st);
+                    if (kt == OP_KT - 1) umma_commit(bar_tfull + as);
+                }
+                __syncwarp();
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0 && *flag && p.status) atomicOr(p.status, CEV_STATUS_NONFINITE);
+    if (warp == 13) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+int rollout_lockstep_launches(int n_cycles) { return 3 + 3 * n_cycles; }
+
+int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t stream) {
+    if (p.P <= 0 || p.K <= 0 || p.E <= 0) return CEV_OK;
+    EncodeTiledFn encode = get_encode_fn();
+    if (!encode) {
+        set_error("rollout_lockstep: cuTensorMapEncodeTiled is not available from the driver");
+        return CEV_ERR_UNSUPPORTED;
+    }
+    const int64_t N = (int64_t)p.P * p.K * p.E;
+    const size_t need = ls_carve(nullptr, N, p.K, nullptr);
+    if (h->ls_workspace_bytes < need) {
+        if (h->ls_workspace) CEV_CUDA(cudaFree(h->ls_workspace));
+        h->ls_workspace = nullptr;
+        h->ls_workspace_bytes = 0;
+        CEV_CUDA(cudaMalloc(&h->ls_workspace, need));
+        h->ls_workspace_bytes = need;
+    }
+    LsBuffers b;
+    ls_carve(h->ls_workspace, N, p.K, &b);
+    const int ms = p.member_seat;
+    const int seat_of[2] = {ms == 0 ? 1 : 0, ms == 2 ? 1 : 2};
+
+    static bool configured[16] = {};
+    if (h->device < 16 && !configured[h->device]) {
+        CEV_CUDA(cudaFuncSetAttribute(ls_member_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)LsMemberSmem::total));
+        CEV_CUDA(cudaFuncSetAttribute(ls_opp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OP_SMEM));
+        configured[h->device] = true;
+    }
+
+    // ---- opponents: TF32 split + layer-1 statistics ------------------------------------------
+    LsPrepParams pp{};
+    for (int oi = 0; oi < 2; ++oi) {
+        pp.opp[oi] = p.opp[oi];
+        pp.opp_pitch[oi] = p.opp_pitch[oi];
+        pp.seat[oi] = seat_of[oi];
+    }
+    pp.K = p.K;
+    pp.w2split = b.w2split;
+    pp.l1stats = b.l1stats;
+    ls_split_w2_kernel<<<dim3(32, 2 * p.K), 256, 0, stream>>>(pp);
+    ls_l1stats_kernel<<<2 * p.K, 128, 0, stream>>>(pp);
+
+    // ---- tensor maps ---------------------------------------------------------------------------
+    CUtensorMap map_w2, map_b;
+    {
+        const FcOffsets om = fc_offsets(seat_in_dim(ms));
+        cuuint64_t dims[3] = {(cuuint64_t)H1, (cuuint64_t)H2, (cuuint64_t)p.P};
+        cuuint64_t strides[2] = {(cuuint64_t)H1 * 4, (cuuint64_t)p.member_pitch * 4};
+        cuuint32_t box[3] = {32, 64, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = encode(&map_w2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.members + om.fc2w), dims,
+                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("rollout_lockstep: cuTensorMapEncodeTiled(member fc2) failed with %d", (int)r);
+            return CEV_ERR_CUDA;
+        }
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)H1, (cuuint64_t)2 * p.K * 2 * H2};
+        cuuint64_t strides[1] = {(cuuint64_t)H1 * 4};
+        cuuint32_t box[2] = {OP_BK, OP_BN};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, b.w2split, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("rollout_lockstep: cuTensorMapEncodeTiled(opponent fc2) failed with %d", (int)r);
+            return CEV_ERR_CUDA;
+        }
+    }
+
+    // ---- per-step parameter blocks ---------------------------------------------------------------
+    LsEnvParams ep{};
+    ep.b = b;
+    ep.N = N;
+    ep.K = p.K;
+    ep.E = p.E;
+    ep.init_shared = p.init_shared;
+    ep.pos_first = p.pos_first;
+    ep.init = p.init;
+    ep.out = p.out;
+    const int env_blocks = (int)((N + 255) / 256);
+
+    LsMemberParams mp{};
+    mp.members = p.members;
+    mp.pitch = p.member_pitch;
+    mp.KE = p.K * p.E;
+    mp.n_chunks = (mp.KE + LS_BT - 1) / LS_BT;
+    mp.seat = ms;
+    mp.N = N;
+    mp.obs = b.obs + (int64_t)ms * N * LS_OBS_PAD;
+    mp.act = b.act + (int64_t)ms * N;
+    mp.gap = b.gap + (int64_t)ms * N;
+    mp.status = p.status;
+    const int64_t member_ctas = (int64_t)p.P * mp.n_chunks;
+    CEV_REQUIRE(member_ctas < (1ll << 31), "rollout_lockstep: too many member tiles");
+
+    LsOppParams op{};
+    for (int oi = 0; oi < 2; ++oi) {
+        op.opp[oi] = p.opp[oi];
+        op.opp_pitch[oi] = p.opp_pitch[oi];
+        op.seat[oi] = seat_of[oi];
+    }
+    op.K = p.K;
+    op.E = p.E;
+    op.PE = (int64_t)p.P * p.E;
+    op.n_tiles = (int)((op.PE + OP_BM - 1) / OP_BM);
+    op.n_jobs = 2 * p.K * op.n_tiles;
+    op.N = N;
+    op.obs = b.obs;
+    op.act = b.act;
+    op.gap = b.gap;
+    op.l1stats = b.l1stats;
+    op.status = p.status;
+    const int opp_grid = op.n_jobs < h->n_sm ? op.n_jobs : h->n_sm;
+
+    ep.last = p.n_cycles == 0;
+    ls_init_kernel<<<env_blocks, 256, 0, stream>>>(ep);
+    for (int c = 0; c < p.n_cycles; ++c) {
+        ls_opp_kernel<<<opp_grid, OP_THREADS, OP_SMEM, stream>>>(map_b, op);
+        ls_member_kernel<<<(unsigned)member_ctas, CT, LsMemberSmem::total, stream>>>(map_w2, mp);
+        ep.last = c == p.n_cycles - 1;
+        ls_env_step_kernel<<<env_blocks, 256, 0, stream>>>(ep);
+    }
+    return check_cuda(cudaGetLastError(), "rollout_lockstep launch");
+}
+
+}  // namespace cev

@@ -16,15 +16,25 @@ from ._lib import RolloutCfg, check, handle, load
 MAX_CYCLES = 25
 
 #: kernels launched per C-ABI call (bench.py reports the total as ``gpu_launches``)
-_KERNELS_PER_CALL = {"cev_es_update_f32": 2, "cev_fp32_peak": 4, "cev_mpe_rollout_f32": 3}
+_KERNELS_PER_CALL = {"cev_es_update_f32": 2, "cev_fp32_peak": 4}
 launch_count = 0
 
 
-def _call(name, *args):
+def _call(name, *args, launches=None):
     """Invoke one C-ABI entry point, counting the CUDA kernels it launches."""
     global launch_count
-    launch_count += _KERNELS_PER_CALL.get(name, 1)
+    launch_count += _KERNELS_PER_CALL.get(name, 1) if launches is None else launches
     return getattr(load(), name)(*args)
+
+
+def rollout_plan(device_index, P, K, E, n_cycles=25, variant=0):
+    """(kernel variant, kernels launched) of one structured rollout of this shape:
+    1 generic, 2 cluster (member weights resident), 3 lockstep (opponents on tcgen05)."""
+    used, n = ctypes.c_int(), ctypes.c_int()
+    check(load().cev_mpe_rollout_plan(handle(device_index), int(P), int(K), int(E), int(n_cycles),
+                                      int(variant), ctypes.byref(used), ctypes.byref(n)),
+          "cev_mpe_rollout_plan")
+    return used.value, n.value
 
 
 def _ptr(t):
@@ -116,11 +126,12 @@ def mpe_rollout(member_role, members, opp_a, opp_b, init, *, n_cycles=MAX_CYCLES
     if out is None:
         out = torch.empty((P, K, E, _lib.ROLLOUT_OUT_DIM), dtype=torch.float64, device=dev)
     cfg = RolloutCfg(int(n_cycles), int(bool(pos_first)), int(variant), 0)
-    check(_call("cev_mpe_rollout_f32", 
+    _, n_launch = rollout_plan(dev.index, P, K, E, n_cycles, variant)
+    check(_call("cev_mpe_rollout_f32",
         handle(dev.index), seat, _ptr(members), P, members.stride(0),
         _ptr(opp_a), opp_a.stride(0), _ptr(opp_b), opp_b.stride(0), K,
         _ptr(init), int(bool(init_shared)), E, ctypes.byref(cfg), _ptr(out), _ptr(status),
-        _stream(dev)), "cev_mpe_rollout_f32")
+        _stream(dev), launches=n_launch), "cev_mpe_rollout_f32")
     return out
 
 

@@ -73,7 +73,8 @@ typedef struct {
                                     under play_MPE's agent-step limit
                                     (utils/game_logic_functions.py:127,195) */
     int32_t integrate_pos_first; /* SURVEY.md Appendix A.4 switch (1 = PettingZoo >= 1.24) */
-    int32_t variant;             /* 0 auto, 1 generic kernel, 2 cluster kernel */
+    int32_t variant;             /* 0 auto, 1 generic kernel, 2 cluster kernel (member weights resident in
+                                    shared memory), 3 lockstep kernels (opponent forwards on tcgen05) */
     int32_t reserved;
 } cev_rollout_cfg;
 
@@ -97,6 +98,13 @@ int cev_mpe_rollout_f32(cev_handle* h, int member_seat,
                         const double* init, int init_shared, int E,
                         const cev_rollout_cfg* cfg,
                         double* out, int32_t* status, cev_stream stream);
+
+/*
+ * Which kernel a structured rollout of this shape uses (variant 0 = the library's choice) and
+ * how many kernels one cev_mpe_rollout_f32 call launches.  Host-only, no device work.
+ */
+int cev_mpe_rollout_plan(cev_handle* h, int P, int K, int E, int n_cycles, int variant,
+                         int* variant_used, int* n_launches);
 
 /*
  * K1 -- indexed form: N independent episodes, episode e played by rows

@@ -84,7 +84,7 @@ def _structured_case(member_role, P, K, E, seed, n_cycles=25, init_shared=False,
     return out.cpu().numpy().reshape(n, 4), ref
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 @pytest.mark.parametrize("member_role,P,K,E", [
     ("agent_0", 5, 1, 16), ("agent_1", 3, 2, 8), ("adversary_0", 4, 1, 4),
     ("agent_0", 2, 3, 1), ("adversary_0", 3, 1, 13), ("agent_1", 2, 1, 21),
@@ -94,7 +94,7 @@ def test_structured_rollout_matches_oracle(variant, member_role, P, K, E):
     _compare(out, ref, f"variant{variant} {member_role} P{P} K{K} E{E}")
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 def test_shared_init_and_short_episodes(variant):
     for n_cycles in (0, 1, 8, 24):
         out, ref = _structured_case("agent_0", 3, 2, 5, seed=77, n_cycles=n_cycles,
@@ -108,8 +108,28 @@ def test_shared_init_and_short_episodes(variant):
 def test_cluster_and_generic_kernels_agree_bitwise_on_safe_episodes():
     a, ref = _structured_case("agent_0", 6, 2, 16, seed=5, variant=1)
     b, _ = _structured_case("agent_0", 6, 2, 16, seed=5, variant=2)
+    c, _ = _structured_case("agent_0", 6, 2, 16, seed=5, variant=3)
     safe = ref["min_gap"] > GAP
     assert np.array_equal(a[safe, :3], b[safe, :3])
+    assert np.array_equal(a[safe, :3], c[safe, :3])
+
+
+@pytest.mark.parametrize("member_role,P,K,E", [("agent_0", 40, 1, 16), ("adversary_0", 17, 2, 9),
+                                               ("agent_1", 300, 1, 1)])
+def test_lockstep_kernels_match_oracle_on_multi_tile_shapes(member_role, P, K, E):
+    """Variant 3 (tcgen05 opponents): more than one 128-episode tile per opponent, a ragged last
+    tile, ragged 16-episode member chunks; 3xTF32 keeps the opponents' logits at fp32 accuracy, so
+    the same margin criterion as the fp32 kernels applies."""
+    out, ref = _structured_case(member_role, P, K, E, seed=4242 + P, variant=3)
+    _compare(out, ref, f"lockstep {member_role} P{P} K{K} E{E}")
+
+
+def test_lockstep_is_the_auto_choice_for_es_shapes_and_counts_its_launches():
+    from coevonet_b200 import ops
+    assert ops.rollout_plan(0, 1024, 1, 16) == (3, 3 + 3 * 25)
+    assert ops.rollout_plan(0, 20, 3, 1)[0] == 2
+    assert ops.rollout_plan(0, 1, 1, 10)[0] == 2
+    assert ops.rollout_plan(0, 1024, 1, 16, variant=2) == (2, 3)
 
 
 def test_indexed_rollout_matches_golden_reference_episodes(golden):
@@ -157,7 +177,7 @@ def test_nonfinite_weights_raise_like_the_reference():
     nets["agent_0"][1, 100] = np.nan
     dev = {r: _padded(nets[r], olayout.OBS_DIM[r]) for r in nets}
     init = torch.from_numpy(mpe_env.draw_initial_states(2 * 4).reshape(2, 1, 4, 11)).cuda()
-    for variant in (1, 2):
+    for variant in (1, 2, 3):
         status = torch.zeros(1, dtype=torch.int32, device="cuda")
         ops.mpe_rollout("agent_0", dev["agent_0"], dev["adversary_0"], dev["agent_1"], init,
                         variant=variant, status=status)
