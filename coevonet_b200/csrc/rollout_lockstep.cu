@@ -35,6 +35,8 @@
 //
 // Arithmetic: member forward fp32 (FFMA); opponent fc2 3xTF32 with fp32 accumulation (error
 // ~1e-6 of the activations' scale, the same order as fp32 summation-order noise); environment fp64.
+#include <stdlib.h>
+
 #include "rollout_common.cuh"
 #include "tc_common.cuh"
 
@@ -261,17 +263,21 @@ __global__ void __launch_bounds__(128) ls_l1stats_kernel(const LsPrepParams p) {
 // member forward (FP32 pipe)
 // ---------------------------------------------------------------------------------------------
 constexpr int LS_BT = 16;                         // episodes per CTA
-constexpr int LS_TILE_BYTES = 64 * 32 * 4;        // [64 rows x 32 k] fp32
+constexpr int LS_TILE_K = 16;                     // k per tile
+constexpr int LS_TILE_BYTES = 64 * LS_TILE_K * 4; // [64 rows x 16 k] fp32 = 4 KB, 64B-swizzled
 constexpr int LS_NSLOT = 16;
-constexpr int LS_NTILE = 64;                      // 4 row quarters x 16 k-tiles per member
+constexpr int LS_TPW = (H1 / LS_TILE_K) / 2;      // 16 tiles per warp: one row quarter, one k half
 constexpr int LS_TAIL_FLOATS = 2056;              // fc2.b | ln2.g | ln2.b | out.W | out.b (+3 pad), contiguous in the row
 constexpr int LS_W1A_FLOATS = H1 * IN_GOOD + 3 * H1;
 
+// Two CTAs per SM (113 KB each): while one CTA is in its latency-bound phases (layer 1, LayerNorm,
+// reductions, launch prologue) the other one keeps the FMA pipe and the HBM stream busy.  The W1
+// block is only needed by layer 1, so ring slots 8..15 alias it.
 struct LsMemberSmem {
     static constexpr size_t off_ring = 0;
+    static constexpr size_t off_w1a = off_ring + (size_t)(LS_NSLOT / 2) * LS_TILE_BYTES;   // = slots 8..15
     static constexpr size_t off_h1p = off_ring + (size_t)LS_NSLOT * LS_TILE_BYTES;
-    static constexpr size_t off_w1a = off_h1p + (size_t)H1 * LS_BT * 4;
-    static constexpr size_t off_tail = off_w1a + (size_t)LS_W1A_FLOATS * 4;
+    static constexpr size_t off_tail = off_h1p + (size_t)H1 * LS_BT * 4;
     static constexpr size_t off_obs = off_tail + (size_t)LS_TAIL_FLOATS * 4;
     static constexpr size_t off_red1 = off_obs + (size_t)LS_BT * 12 * 4;
     static constexpr size_t off_red = off_red1 + (size_t)2 * NW * LS_BT * 4;
@@ -279,6 +285,8 @@ struct LsMemberSmem {
     static constexpr size_t off_bar = off_flag + 16;
     static constexpr size_t total = off_bar + (size_t)(LS_NSLOT + 2) * 8 + 1024 /*alignment slack*/;
 };
+static_assert((size_t)LS_W1A_FLOATS * 4 <= (size_t)(LS_NSLOT / 2) * LS_TILE_BYTES, "W1 block must fit the aliased slots");
+static_assert(2 * (LsMemberSmem::total + 1024) <= 233472, "two member CTAs must fit one SM");
 
 struct LsMemberParams {
     const float* members;
@@ -291,27 +299,28 @@ struct LsMemberParams {
     int32_t* status;
 };
 
-// One [64 rows x 32 k] tile of fc2 for one warp: lane = (eg = lane % 4: 4 envs, rl = lane / 4: row lane),
-// rows rl + 8 i (i < 8).  Tile rows are 128 bytes, 16-byte chunk c of row r stored at c ^ (r & 7)
-// (TMA SWIZZLE_128B): the 8 row lanes of a load hit 8 distinct bank groups.
+// One [64 rows x 16 k] tile of fc2 for one warp: lane = (eg = lane % 4: 4 envs, rl = lane / 4: row lane),
+// rows rl + 8 i (i < 8).  Tile rows are 64 bytes, 16-byte chunk c of row r stored at c ^ ((r >> 1) & 3)
+// (TMA SWIZZLE_64B): the 8 row lanes of a load hit 8 distinct bank groups.
 __device__ __forceinline__ void ls_fc2_tile(const float4* __restrict__ tile, const float* __restrict__ h1p, int kbase,
                                             float2 (&acc)[8][4]) {
     const int lane = threadIdx.x & 31;
     const int eg = lane & 3, rl = lane >> 2;
-    const float4* wrow0 = tile + rl * 8;
+    const int sw = (rl >> 1) & 3;
+    const float4* wrow0 = tile + rl * 4;
     const float* hbase = h1p + (kbase >> 1) * (2 * LS_BT) + eg * 8;
 #pragma unroll
-    for (int st = 0; st < 8; ++st) {
+    for (int st = 0; st < LS_TILE_K / 4; ++st) {
         float4 a[2][2];
 #pragma unroll
         for (int kp = 0; kp < 2; ++kp)
 #pragma unroll
             for (int j = 0; j < 2; ++j)
                 a[kp][j] = *reinterpret_cast<const float4*>(hbase + (2 * st + kp) * (2 * LS_BT) + j * 4);
-        const int col = st ^ rl;
+        const int col = st ^ sw;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float4 w = wrow0[i * 64 + col];
+            const float4 w = wrow0[i * 32 + col];
             const float2 w0 = make_float2(w.x, w.y), w1 = make_float2(w.z, w.w);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -324,18 +333,19 @@ __device__ __forceinline__ void ls_fc2_tile(const float4* __restrict__ tile, con
     }
 }
 
-__global__ void __launch_bounds__(CT, 1)
+__global__ void __launch_bounds__(CT, 2)
 ls_member_kernel(const __grid_constant__ CUtensorMap map_w2, const LsMemberParams p) {
     using L = LsMemberSmem;
     constexpr int BT = LS_BT;
     constexpr int G = CT / BT;       // 16 row groups
     constexpr int RP = H2 / G;       // 16 fc2 rows per thread after the k-split reduce
+    // 1024-byte alignment for the swizzled TMA tiles, computed as an OFFSET into the __shared__ array so
+    // the compiler keeps the shared address space (LDS/STS, not generic LD/ST)
     extern __shared__ unsigned char ls_raw[];
-    unsigned char* smem =
-        reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ls_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* smem = ls_raw + ((1024u - (smem_u32(ls_raw) & 1023u)) & 1023u);
     unsigned char* ring = smem + L::off_ring;
     float* h1p = reinterpret_cast<float*>(smem + L::off_h1p);        // activations, later the k-split partials
-    float* w1a = reinterpret_cast<float*>(smem + L::off_w1a);
+    float* w1a = reinterpret_cast<float*>(smem + L::off_w1a);        // aliases ring slots 8..15
     float* tail = reinterpret_cast<float*>(smem + L::off_tail);
     float* obs = reinterpret_cast<float*>(smem + L::off_obs);
     float* red1 = reinterpret_cast<float*>(smem + L::off_red1);
@@ -361,20 +371,20 @@ ls_member_kernel(const __grid_constant__ CUtensorMap map_w2, const LsMemberParam
         mbar_fence_init();
     }
     __syncthreads();
-    // tile sequence s = i * 8 + w: the i-th tile of warp w = row quarter (w & 3), k-tile (w >> 2) * 8 + i;
+    // tile sequence s = i * 8 + w: the i-th tile of warp w = row quarter (w & 3), k-tile (w >> 2) * 16 + i;
     // it lives in slot s % 16, so warp w double-buffers its own stream in slots w and w + 8.
     auto issue_tile = [&](int s) {
         const int w = s & 7, i = s >> 3, slot = s & (LS_NSLOT - 1);
-        const int kt = (w >> 2) * 8 + i, rq = w & 3;
+        const int kt = (w >> 2) * LS_TPW + i, rq = w & 3;
         mbar_arrive_expect_tx(bar_tile + slot, LS_TILE_BYTES);
-        tma_load_3d(ring + (size_t)slot * LS_TILE_BYTES, &map_w2, bar_tile + slot, kt * 32, rq * 64, m);
+        tma_load_3d(ring + (size_t)slot * LS_TILE_BYTES, &map_w2, bar_tile + slot, kt * LS_TILE_K, rq * 64, m);
     };
     if (t == 0) {
         const uint32_t w1_bytes = (uint32_t)(H1 * in_dim + 3 * H1) * 4;
         mbar_arrive_expect_tx(bar_w1, w1_bytes);
         bulk_g2s(w1a, mrow, w1_bytes, bar_w1);
 #pragma unroll 1
-        for (int s = 0; s < LS_NSLOT; ++s) issue_tile(s);
+        for (int s = 0; s < LS_NSLOT / 2; ++s) issue_tile(s);      // every warp's first tile (slots 0..7)
         mbar_arrive_expect_tx(bar_tail, LS_TAIL_FLOATS * 4);
         bulk_g2s(tail, mrow + om.fc2b, LS_TAIL_FLOATS * 4, bar_tail);
     }
@@ -387,22 +397,26 @@ ls_member_kernel(const __grid_constant__ CUtensorMap map_w2, const LsMemberParam
     mbar_wait(bar_w1, 0);
     if (p.seat == 0) layer1<BT, IN_ADV>(w1a, obs, h1p, red1, flag);
     else layer1<BT, IN_GOOD>(w1a, obs, h1p, red1, flag);
-    __syncthreads();
+    __syncthreads();          // h1p complete; the W1 block is dead, slots 8..15 are free
+    if (lane == 0) {
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic reads of W1 before the TMA writes
+        issue_tile(8 + warp);
+    }
 
-    // ---- fc2: warp w = (row quarter w & 3, k half w >> 2), 8 tiles of [64 x 32] ----------------
+    // ---- fc2: warp w = (row quarter w & 3, k half w >> 2), 16 tiles of [64 x 16] ---------------
     float2 acc[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
 #pragma unroll 1
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < LS_TPW; ++i) {
         const int slot = warp + 8 * (i & 1);
         mbar_wait(bar_tile + slot, (uint32_t)(i >> 1));
         ls_fc2_tile(reinterpret_cast<const float4*>(ring + (size_t)slot * LS_TILE_BYTES), h1p,
-                    ((warp >> 2) * 8 + i) * 32, acc);
+                    ((warp >> 2) * LS_TPW + i) * LS_TILE_K, acc);
         __syncwarp();
-        if (lane == 0 && i + 2 < 8) issue_tile((i + 2) * 8 + warp);
+        if (lane == 0 && i + 2 < LS_TPW) issue_tile((i + 2) * 8 + warp);
     }
     __syncthreads();          // every warp is done reading h1p
     {
@@ -506,8 +520,11 @@ constexpr uint32_t OP_B_BYTES = OP_BN * OP_BK * 4;          // 32 KB
 constexpr uint32_t OP_STAGE_BYTES = 2 * OP_A_BYTES + 2 * OP_B_BYTES;   // A hi | A lo | B hi | B lo = 96 KB
 constexpr int OP_STAGES = 2;
 constexpr size_t OP_OFF_W1A = (size_t)OP_STAGES * OP_STAGE_BYTES;
-constexpr size_t OP_OFF_BAR = OP_OFF_W1A + (size_t)LS_W1A_FLOATS * 4;
-constexpr size_t OP_SMEM = OP_OFF_BAR + 256 + 1024 /*alignment slack*/;
+constexpr size_t OP_OFF_TAIL = OP_OFF_W1A + (size_t)LS_W1A_FLOATS * 4;      // fc2.b | ln2.g | ln2.b | out.W | out.b
+constexpr size_t OP_OFF_BAR = OP_OFF_TAIL + (size_t)LS_TAIL_FLOATS * 4;
+constexpr size_t OP_SMEM_MAX = 232448;                                     // 227 KB opt-in limit per CTA
+constexpr size_t OP_SLACK = OP_SMEM_MAX - (OP_OFF_BAR + 128);              // what is left for the 1024-byte alignment
+constexpr size_t OP_SMEM = OP_SMEM_MAX;
 constexpr uint32_t OP_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(OP_BN >> 3) << 17) |
                               ((uint32_t)(OP_BM >> 4) << 24);
 
@@ -538,8 +555,8 @@ __device__ __forceinline__ void op_umma(uint32_t d_tmem, uint64_t a_desc, uint64
 // the 128-byte swizzle the UMMA descriptor expects (chunk c of row r at c ^ (r & 7)).
 template <int IN>
 __device__ __forceinline__ void op_produce_half(const float* __restrict__ w1a, const float (&x)[LS_OBS_PAD], float mean,
-                                                float rstd, int kt, int half, int r, unsigned char* a_hi,
-                                                unsigned char* a_lo) {
+                                                float rstd, int kt, int half, int r, unsigned char* __restrict__ a_hi,
+                                                unsigned char* __restrict__ a_lo) {
     const float* fc1b = w1a + H1 * IN;
     const float* ln1g = fc1b + H1;
     const float* ln1b = ln1g + H1;
@@ -564,8 +581,10 @@ __device__ __forceinline__ void op_produce_half(const float* __restrict__ w1a, c
             }
             pre += bq[qq];
             const float h = fmaxf(fmaf((pre - mean) * rstd, gq[qq], eq[qq]), 0.f);
-            hi[qq] = tf32_rna(h);
-            lo[qq] = tf32_rna(h - hi[qq]);
+            // hi = h truncated to TF32 (exactly what the tensor core reads of an fp32 word); lo = h - hi is
+            // exact in fp32 and is itself read truncated: relative error 2^-21, like the dropped lo.lo term
+            hi[qq] = __uint_as_float(__float_as_uint(h) & 0xffffe000u);
+            lo[qq] = h - hi[qq];
         }
         const int off = (c ^ (r & 7)) << 4;
         *reinterpret_cast<float4*>(a_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
@@ -576,10 +595,12 @@ __device__ __forceinline__ void op_produce_half(const float* __restrict__ w1a, c
 __global__ void __launch_bounds__(OP_THREADS, 1)
 ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
     extern __shared__ unsigned char op_raw[];
-    unsigned char* base =
-        reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(op_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t pad = (1024u - (smem_u32(op_raw) & 1023u)) & 1023u;
+    if (pad > OP_SLACK) __trap();          // dynamic shared memory starts 1 KB aligned on sm_100; checked, not assumed
+    unsigned char* base = op_raw + pad;    // offset into the __shared__ array: keeps the shared address space
     unsigned char* stage_mem = base;
     float* w1a = reinterpret_cast<float*>(base + OP_OFF_W1A);
+    float* tail = reinterpret_cast<float*>(base + OP_OFF_TAIL);
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(base + OP_OFF_BAR);   // [2] A written + B landed
     uint64_t* bar_empty = bar_full + OP_STAGES;                             // [2] MMAs retired
     uint64_t* bar_tfull = bar_empty + OP_STAGES;                            // [2] accumulator ready
@@ -617,17 +638,26 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
         // ===================== epilogue: bias + LayerNorm-2 + ReLU + output layer + argmax =====
         const int q = warp;
         uint32_t pass = 0;
+        int cur_ok = -1;
+        const float* b2 = tail;
+        const float* g2 = tail + H2;
+        const float* be2 = tail + 2 * H2;
+        const float* w3 = tail + 3 * H2;
+        const float* b3 = tail + 3 * H2 + NACT * H2;
         for (int job = blockIdx.x; job < p.n_jobs; job += gridDim.x, ++pass) {
             const int okey = job / jobs_per_ok, tile = job % jobs_per_ok;
             const int oi = okey / p.K, k = okey % p.K;
-            const int seat = p.seat[oi];
-            const FcOffsets o = fc_offsets(seat_in_dim(seat));
-            const float* row = p.opp[oi] + (int64_t)k * p.opp_pitch[oi];
-            const float* b2 = row + o.fc2b;
-            const float* g2 = row + o.ln2g;
-            const float* be2 = row + o.ln2b;
-            const float* w3 = row + o.outw;
-            const float* b3 = row + o.outb;
+            const int seat = oi ? p.seat[1] : p.seat[0];
+            if (okey != cur_ok) {
+                // this opponent's epilogue parameters -> shared memory (only the epilogue warps touch them)
+                const float* row = (oi ? p.opp[1] : p.opp[0]) + (int64_t)k * (oi ? p.opp_pitch[1] : p.opp_pitch[0]);
+                const float4* src = reinterpret_cast<const float4*>(row + fc_offsets(seat_in_dim(seat)).fc2b);
+                asm volatile("bar.sync 2, 128;\n" ::: "memory");
+                for (int f = threadIdx.x; f < LS_TAIL_FLOATS / 4; f += 128)
+                    reinterpret_cast<float4*>(tail)[f] = __ldg(src + f);
+                asm volatile("bar.sync 2, 128;\n" ::: "memory");
+                cur_ok = okey;
+            }
             const int64_t j = (int64_t)tile * OP_BM + q * 32 + lane;
             const bool valid = j < p.PE;
             const int64_t jj = valid ? j : p.PE - 1;
@@ -642,7 +672,13 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
                 uint32_t v[32];
                 tmem_ld32(taddr + c0, v);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) sum += __uint_as_float(v[i]) + __ldg(b2 + c0 + i);
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 bb = *reinterpret_cast<const float4*>(b2 + c0 + i);
+                    sum += __uint_as_float(v[i]) + bb.x;
+                    sum += __uint_as_float(v[i + 1]) + bb.y;
+                    sum += __uint_as_float(v[i + 2]) + bb.z;
+                    sum += __uint_as_float(v[i + 3]) + bb.w;
+                }
             }
             const float mean = sum * (1.0f / H2);
             float sq = 0.f;
@@ -651,9 +687,14 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
                 uint32_t v[32];
                 tmem_ld32(taddr + c0, v);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float d = (__uint_as_float(v[i]) + __ldg(b2 + c0 + i)) - mean;
-                    sq = fmaf(d, d, sq);
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 bb = *reinterpret_cast<const float4*>(b2 + c0 + i);
+                    const float bq[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float d = (__uint_as_float(v[i + u]) + bq[u]) - mean;
+                        sq = fmaf(d, d, sq);
+                    }
                 }
             }
             const float var = sq * (1.0f / H2);
@@ -664,12 +705,27 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
                 uint32_t v[32];
                 tmem_ld32(taddr + c0, v);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
+                for (int i = 0; i < 32; i += 4) {
                     const int c = c0 + i;
-                    const float x = (__uint_as_float(v[i]) + __ldg(b2 + c)) - mean;
-                    const float h = fmaxf(fmaf(x * rstd, __ldg(g2 + c), __ldg(be2 + c)), 0.f);
+                    const float4 bb = *reinterpret_cast<const float4*>(b2 + c);
+                    const float4 gg = *reinterpret_cast<const float4*>(g2 + c);
+                    const float4 ee = *reinterpret_cast<const float4*>(be2 + c);
+                    const float bq[4] = {bb.x, bb.y, bb.z, bb.w}, gq[4] = {gg.x, gg.y, gg.z, gg.w},
+                                eq[4] = {ee.x, ee.y, ee.z, ee.w};
+                    float h[4];
 #pragma unroll
-                    for (int a = 0; a < NACT; ++a) lg[a] = fmaf(__ldg(w3 + a * H2 + c), h, lg[a]);
+                    for (int u = 0; u < 4; ++u) {
+                        const float x = (__uint_as_float(v[i + u]) + bq[u]) - mean;
+                        h[u] = fmaxf(fmaf(x * rstd, gq[u], eq[u]), 0.f);
+                    }
+#pragma unroll
+                    for (int a = 0; a < NACT; ++a) {
+                        const float4 ww = *reinterpret_cast<const float4*>(w3 + a * H2 + c);
+                        lg[a] = fmaf(ww.x, h[0], lg[a]);
+                        lg[a] = fmaf(ww.y, h[1], lg[a]);
+                        lg[a] = fmaf(ww.z, h[2], lg[a]);
+                        lg[a] = fmaf(ww.w, h[3], lg[a]);
+                    }
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -678,7 +734,7 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
             bool fin = isfinite(mean) && isfinite(var);
 #pragma unroll
             for (int a = 0; a < NACT; ++a) {
-                lg[a] += __ldg(b3 + a);
+                lg[a] += b3[a];
                 fin = fin && isfinite(lg[a]);
             }
             float gap;
@@ -698,9 +754,9 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
         for (int job = blockIdx.x; job < p.n_jobs; job += gridDim.x) {
             const int okey = job / jobs_per_ok, tile = job % jobs_per_ok;
             const int oi = okey / p.K, k = okey % p.K;
-            const int seat = p.seat[oi];
+            const int seat = oi ? p.seat[1] : p.seat[0];
             const int in = seat_in_dim(seat);
-            const float* row = p.opp[oi] + (int64_t)k * p.opp_pitch[oi];
+            const float* row = (oi ? p.opp[1] : p.opp[0]) + (int64_t)k * (oi ? p.opp_pitch[1] : p.opp_pitch[0]);
             if (okey != cur_ok) {
                 asm volatile("bar.sync 1, 256;\n" ::: "memory");       // producers done with the old block
                 const int n4 = (H1 * in + 3 * H1) / 4;
@@ -838,6 +894,7 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
     if (h->device < 16 && !configured[h->device]) {
         CEV_CUDA(cudaFuncSetAttribute(ls_member_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)LsMemberSmem::total));
+        CEV_CUDA(cudaFuncSetAttribute(ls_member_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CEV_CUDA(cudaFuncSetAttribute(ls_opp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OP_SMEM));
         configured[h->device] = true;
     }
@@ -861,10 +918,10 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
         const FcOffsets om = fc_offsets(seat_in_dim(ms));
         cuuint64_t dims[3] = {(cuuint64_t)H1, (cuuint64_t)H2, (cuuint64_t)p.P};
         cuuint64_t strides[2] = {(cuuint64_t)H1 * 4, (cuuint64_t)p.member_pitch * 4};
-        cuuint32_t box[3] = {32, 64, 1};
+        cuuint32_t box[3] = {LS_TILE_K, 64, 1};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = encode(&map_w2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.members + om.fc2w), dims,
-                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             set_error("rollout_lockstep: cuTensorMapEncodeTiled(member fc2) failed with %d", (int)r);
@@ -930,11 +987,15 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
     op.status = p.status;
     const int opp_grid = op.n_jobs < h->n_sm ? op.n_jobs : h->n_sm;
 
+    // development aid (timing only, results are then invalid): CEV_LS_SKIP bit 0 = no opponent kernel,
+    // bit 1 = no member kernel
+    static const int skip = getenv("CEV_LS_SKIP") ? atoi(getenv("CEV_LS_SKIP")) : 0;
     ep.last = p.n_cycles == 0;
     ls_init_kernel<<<env_blocks, 256, 0, stream>>>(ep);
     for (int c = 0; c < p.n_cycles; ++c) {
-        ls_opp_kernel<<<opp_grid, OP_THREADS, OP_SMEM, stream>>>(map_b, op);
-        ls_member_kernel<<<(unsigned)member_ctas, CT, LsMemberSmem::total, stream>>>(map_w2, mp);
+        if (!(skip & 1)) ls_opp_kernel<<<opp_grid, OP_THREADS, OP_SMEM, stream>>>(map_b, op);
+        if (!(skip & 2))
+            ls_member_kernel<<<(unsigned)member_ctas, CT, LsMemberSmem::total, stream>>>(map_w2, mp);
         ep.last = c == p.n_cycles - 1;
         ls_env_step_kernel<<<env_blocks, 256, 0, stream>>>(ep);
     }
