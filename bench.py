@@ -221,6 +221,8 @@ def run_gpu_arm(ns):
     for _ in range(ns.warmup):
         eng.step()
     barrier()
+    k1_variant, k1_launches = ops.rollout_plan(local, n_local, 1, ENVS, CYCLES)
+    ops.kernel_timing_enable(local, True)      # CUDA events around the member / opponent kernels of K1
     eng.k1_events = []
     sampler = ClockSampler(local)
     if rank == 0:
@@ -238,6 +240,9 @@ def run_gpu_arm(ns):
     ms_total = e0.elapsed_time(e1)
     k1_ms = [a.elapsed_time(b) for a, b in eng.k1_events]
     eng.k1_events = None
+    member_ms, member_n = ops.kernel_timing_read(local, 0)
+    opp_ms, opp_n = ops.kernel_timing_read(local, 1)
+    ops.kernel_timing_enable(local, False)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -287,26 +292,61 @@ def run_gpu_arm(ns):
         fp32_peak = max(ops.fp32_peak(dev, 0), ops.fp32_peak(dev, 1))
         k1_avg_ms = float(np.mean(k1_ms))
         k1_flop = n_local * ENVS * CYCLES * FLOP_PER_WORLD_STEP
-        achieved = k1_flop / (k1_avg_ms * 1e-3) / 1e12
         traffic = _k1_traffic()
+        hbm_peak = float(peaks["hbm_gbs"])
+        tf32_peak = float(peaks["bf16_tflops"]) / 2.0
+        k1_block = {"k1_variant": {1: "generic", 2: "cluster", 3: "lockstep"}[k1_variant],
+                    "k1_kernels_per_call": k1_launches, "k1_ms_per_call": k1_avg_ms, "k1_calls_timed": len(k1_ms),
+                    "k1_share_of_step": sum(k1_ms) / ms_total if world == 1 else None,
+                    "k1_algorithmic_tflops": k1_flop / (k1_avg_ms * 1e-3) / 1e12,
+                    "k1_algorithmic_flop_per_call": k1_flop,
+                    "fp32_peak_tflops": fp32_peak,
+                    "fp32_peak_source": "FP32 FMA-pipe peak measured live by cev_fp32_peak (MEASURED_PEAKS.json "
+                                        "has no FP32 figure)"}
+        if k1_variant == 3 and member_n > 0:
+            # dominant kernel: ls_member_kernel, one launch per world step; it streams every member row once
+            # per launch (algorithmic bytes = rows x D x 4, D averaged over the three roles' launches)
+            row_bytes = 4.0 * sum(layout.fc_dim(layout.OBS_DIM[r]) for r in ROLES) / 3.0
+            member_us = member_ms / member_n * 1e3
+            opp_us = opp_ms / max(opp_n, 1) * 1e3
+            alg_bytes = n_local * row_bytes
+            achieved = alg_bytes / (member_us * 1e-6) / 1e9
+            member_flop = n_local * ENVS * (2 * 274944 + 272896) / 3.0
+            opp_flop = 2.0 * n_local * ENVS * 2 * 512 * 256          # fc2 of the two opponent seats
+            roof = {"kernel": "ls_member_kernel (K1 lockstep, member forward; one launch per world step)",
+                    "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": achieved / hbm_peak,
+                    "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks_src})",
+                    "us_per_launch": member_us, "launches_timed": member_n,
+                    "share_of_step": member_ms / ms_total if world == 1 else None,
+                    "algorithmic_bytes_per_launch": alg_bytes,
+                    "algorithmic_bytes_per_unit": row_bytes, "unit_def": "member row per world step",
+                    "fp32_tflops": member_flop / (member_us * 1e-6) / 1e12,
+                    "fp32_frac": member_flop / (member_us * 1e-6) / 1e12 / fp32_peak,
+                    "traffic": traffic["dram_bytes_per_launch"] * n_local / traffic["members"] if traffic else None,
+                    "traffic_source": traffic["source"] if traffic else None,
+                    "second_kernel": {
+                        "kernel": "ls_opp_kernel (tcgen05 kind::tf32, 3 MMAs per product = 3xTF32)",
+                        "bound": "tensor", "us_per_launch": opp_us, "launches_timed": opp_n,
+                        "share_of_step": opp_ms / ms_total if world == 1 else None,
+                        "achieved": opp_flop / (opp_us * 1e-6) / 1e12, "unit": "TFLOP/s",
+                        "issued_tf32_tflops": 3 * opp_flop / (opp_us * 1e-6) / 1e12,
+                        "peak": tf32_peak, "frac": 3 * opp_flop / (opp_us * 1e-6) / 1e12 / tf32_peak,
+                        "peak_source": f"half of MEASURED_PEAKS.json bf16_tflops ({peaks_src}): dense TF32 runs at "
+                                       "half the bf16 rate; frac counts the 3 issued MMAs per algorithmic product"}}
+        else:
+            achieved = k1_flop / (k1_avg_ms * 1e-3) / 1e12
+            roof = {"kernel": "rollout_cluster_kernel<16> (K1)", "bound": "fp32", "achieved": achieved,
+                    "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+                    "traffic": None}
+        roof.update(k1_block)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": ns.steps,
             "warmup": ns.warmup, "ms_per_step": ms_total / ns.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": _config(world),
             "agent_steps_per_sec": 3 * value,
-            "roofline": {
-                "kernel": "rollout_cluster_kernel<16> (K1)", "bound": "fp32",
-                "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                "peak_source": "FP32 FMA-pipe peak measured live by cev_fp32_peak (SURVEY.md 8d: "
-                               "K1 is bound by the FP32 pipe; MEASURED_PEAKS.json has no FP32 figure)",
-                "frac_of_bf16_tensor_peak": achieved / peaks["bf16_tflops"],
-                "tensor_peak_source": f"MEASURED_PEAKS.json bf16_tflops ({peaks_src})",
-                "k1_ms_per_launch": k1_avg_ms, "k1_launches_timed": len(k1_ms),
-                "k1_share_of_step": sum(k1_ms) / ms_total if world == 1 else None,
-                "algorithmic_flop_per_launch": k1_flop,
-                "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
-                "traffic_source": traffic["source"] if traffic else None},
+            "roofline": roof,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps},
             "gpu_launches": launches,

@@ -46,6 +46,8 @@ _SIGNATURES = {
                                     c_void_p, c_int, c_int, POINTER(RolloutCfg),
                                     c_void_p, c_void_p, c_void_p]),
     "cev_mpe_rollout_plan": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]),
+    "cev_kernel_timing_enable": (c_int, [c_void_p, c_int]),
+    "cev_kernel_timing_read": (c_int, [c_void_p, c_int, POINTER(c_double), POINTER(c_int)]),
     "cev_mpe_rollout_indexed_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                                             c_void_p, c_int64, c_void_p, c_void_p, c_int,
                                             POINTER(RolloutCfg), c_void_p, c_void_p, c_void_p]),

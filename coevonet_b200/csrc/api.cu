@@ -55,6 +55,9 @@ int cev_create(int device, cev_handle** out) {
     h->opp_workspace_bytes = 0;
     h->ls_workspace = nullptr;
     h->ls_workspace_bytes = 0;
+    h->timing_on = 0;
+    h->timing_n[0] = h->timing_n[1] = 0;
+    h->timing_ev[0] = h->timing_ev[1] = nullptr;
     int ncl = rollout_cluster_max_clusters(device);
     if (ncl <= 0) ncl = h->n_sm / 4 - 4;
     h->n_clusters = ncl;
@@ -67,6 +70,11 @@ int cev_destroy(cev_handle* h) {
     if (h->workspace) cudaFree(h->workspace);
     if (h->opp_workspace) cudaFree(h->opp_workspace);
     if (h->ls_workspace) cudaFree(h->ls_workspace);
+    for (int k = 0; k < 2; ++k)
+        if (h->timing_ev[k]) {
+            for (int i = 0; i < 2 * CEV_TIMING_MAX; ++i) cudaEventDestroy(h->timing_ev[k][i]);
+            delete[] h->timing_ev[k];
+        }
     delete h;
     return CEV_OK;
 }
@@ -170,6 +178,35 @@ int cev_mpe_rollout_plan(cev_handle* h, int P, int K, int E, int n_cycles, int v
     const int v = rollout_plan(h, P, K, E, variant);
     if (variant_used) *variant_used = v;
     if (n_launches) *n_launches = v == 3 ? rollout_lockstep_launches(n_cycles) : (v == 2 ? 3 : 1);
+    return CEV_OK;
+}
+
+int cev_kernel_timing_enable(cev_handle* h, int on) {
+    CEV_REQUIRE(h != nullptr, "kernel_timing_enable: null handle");
+    if (on && !h->timing_ev[0]) {
+        for (int k = 0; k < 2; ++k) {
+            h->timing_ev[k] = new cudaEvent_t[2 * CEV_TIMING_MAX];
+            for (int i = 0; i < 2 * CEV_TIMING_MAX; ++i) CEV_CUDA(cudaEventCreate(&h->timing_ev[k][i]));
+        }
+    }
+    h->timing_on = on ? 1 : 0;
+    h->timing_n[0] = h->timing_n[1] = 0;
+    return CEV_OK;
+}
+
+int cev_kernel_timing_read(cev_handle* h, int which, double* total_ms, int* n_launches) {
+    CEV_REQUIRE(h != nullptr && (which == 0 || which == 1), "kernel_timing_read: bad arguments");
+    double tot = 0.0;
+    const int n = h->timing_n[which];
+    for (int i = 0; i < n; ++i) {
+        CEV_CUDA(cudaEventSynchronize(h->timing_ev[which][2 * i + 1]));
+        float ms = 0.f;
+        CEV_CUDA(cudaEventElapsedTime(&ms, h->timing_ev[which][2 * i], h->timing_ev[which][2 * i + 1]));
+        tot += ms;
+    }
+    if (total_ms) *total_ms = tot;
+    if (n_launches) *n_launches = n;
+    h->timing_n[which] = 0;
     return CEV_OK;
 }
 

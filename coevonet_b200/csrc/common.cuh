@@ -227,6 +227,8 @@ __host__ __device__ __forceinline__ uint32_t noise_tag(int kind, int role) {
 
 }  // namespace cev
 
+constexpr int CEV_TIMING_MAX = 4096;
+
 // per-handle state
 struct cev_handle {
     int device;
@@ -238,6 +240,11 @@ struct cev_handle {
     size_t opp_workspace_bytes;
     void* ls_workspace;    // episode state / split opponent weights of the lockstep rollout
     size_t ls_workspace_bytes;
+    // optional per-kernel timing of the lockstep rollout (cev_kernel_timing_*): CUDA events recorded
+    // around every member / opponent kernel launch on the launch stream
+    int timing_on;
+    int timing_n[2];                    // events pairs used so far: 0 = member kernel, 1 = opponent kernel
+    cudaEvent_t* timing_ev[2];          // [CEV_TIMING_MAX][2] each
 };
 
 // ---------------------------------------------------------------------------

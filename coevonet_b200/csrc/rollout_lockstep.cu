@@ -993,9 +993,23 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
     ep.last = p.n_cycles == 0;
     ls_init_kernel<<<env_blocks, 256, 0, stream>>>(ep);
     for (int c = 0; c < p.n_cycles; ++c) {
-        if (!(skip & 1)) ls_opp_kernel<<<opp_grid, OP_THREADS, OP_SMEM, stream>>>(map_b, op);
-        if (!(skip & 2))
+        // optional per-kernel CUDA-event timing on the launch stream (cev_kernel_timing_enable)
+        auto tick = [&](int which, int end) {
+            if (h->timing_on && h->timing_n[which] < CEV_TIMING_MAX) {
+                cudaEventRecord(h->timing_ev[which][2 * h->timing_n[which] + end], stream);
+                if (end) ++h->timing_n[which];
+            }
+        };
+        if (!(skip & 1)) {
+            tick(1, 0);
+            ls_opp_kernel<<<opp_grid, OP_THREADS, OP_SMEM, stream>>>(map_b, op);
+            tick(1, 1);
+        }
+        if (!(skip & 2)) {
+            tick(0, 0);
             ls_member_kernel<<<(unsigned)member_ctas, CT, LsMemberSmem::total, stream>>>(map_w2, mp);
+            tick(0, 1);
+        }
         ep.last = c == p.n_cycles - 1;
         ls_env_step_kernel<<<env_blocks, 256, 0, stream>>>(ep);
     }

@@ -100,6 +100,20 @@ def raise_on_status(status):
         raise ValueError("\n\t Warning: output contains inf or NaN")
 
 
+def kernel_timing_enable(device_index, on=True):
+    """Record CUDA events around every member / opponent kernel of the lockstep rollout."""
+    check(load().cev_kernel_timing_enable(handle(device_index), int(bool(on))), "cev_kernel_timing_enable")
+
+
+def kernel_timing_read(device_index, which):
+    """(summed device ms, launches) of the member (which=0) or opponent (which=1) kernel since the
+    last read.  Synchronises on the recorded events."""
+    ms, n = ctypes.c_double(), ctypes.c_int()
+    check(load().cev_kernel_timing_read(handle(device_index), int(which), ctypes.byref(ms), ctypes.byref(n)),
+          "cev_kernel_timing_read")
+    return ms.value, n.value
+
+
 def mpe_rollout(member_role, members, opp_a, opp_b, init, *, n_cycles=MAX_CYCLES,
                 pos_first=True, init_shared=False, variant=0, out=None, status=None):
     """K1 structured rollout.

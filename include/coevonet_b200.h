@@ -107,6 +107,15 @@ int cev_mpe_rollout_plan(cev_handle* h, int P, int K, int E, int n_cycles, int v
                          int* variant_used, int* n_launches);
 
 /*
+ * Measurement aid: when enabled, the lockstep rollout (variant 3) records CUDA events around every
+ * member-forward (which = 0) and opponent-forward (which = 1) kernel launch on the launch stream.
+ * cev_kernel_timing_read waits for them, returns the summed device time and the launch count since
+ * the last read, and resets the counters.  At most 4096 launches of each kind are kept per read.
+ */
+int cev_kernel_timing_enable(cev_handle* h, int on);
+int cev_kernel_timing_read(cev_handle* h, int which, double* total_ms, int* n_launches);
+
+/*
  * K1 -- indexed form: N independent episodes, episode e played by rows
  * idx[e] = (adversary_0 row, agent_0 row, agent_1 row).  The batched
  * equivalent of N calls of play_game (utils/game_logic_functions.py:215).
