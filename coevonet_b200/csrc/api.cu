@@ -55,6 +55,8 @@ int cev_create(int device, cev_handle** out) {
     h->opp_workspace_bytes = 0;
     h->ls_workspace = nullptr;
     h->ls_workspace_bytes = 0;
+    h->side_stream = nullptr;
+    h->fork_ev = h->join_ev = nullptr;
     h->timing_on = 0;
     h->timing_n[0] = h->timing_n[1] = 0;
     h->timing_ev[0] = h->timing_ev[1] = nullptr;
@@ -70,6 +72,11 @@ int cev_destroy(cev_handle* h) {
     if (h->workspace) cudaFree(h->workspace);
     if (h->opp_workspace) cudaFree(h->opp_workspace);
     if (h->ls_workspace) cudaFree(h->ls_workspace);
+    if (h->side_stream) {
+        cudaStreamDestroy(h->side_stream);
+        cudaEventDestroy(h->fork_ev);
+        cudaEventDestroy(h->join_ev);
+    }
     for (int k = 0; k < 2; ++k)
         if (h->timing_ev[k]) {
             for (int i = 0; i < 2 * CEV_TIMING_MAX; ++i) cudaEventDestroy(h->timing_ev[k][i]);

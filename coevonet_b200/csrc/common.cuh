@@ -240,6 +240,8 @@ struct cev_handle {
     size_t opp_workspace_bytes;
     void* ls_workspace;    // episode state / split opponent weights of the lockstep rollout
     size_t ls_workspace_bytes;
+    cudaStream_t side_stream;           // the opponent kernel of the lockstep rollout runs beside the member kernel
+    cudaEvent_t fork_ev, join_ev;
     // optional per-kernel timing of the lockstep rollout (cev_kernel_timing_*): CUDA events recorded
     // around every member / opponent kernel launch on the launch stream
     int timing_on;
