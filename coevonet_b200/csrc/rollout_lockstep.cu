@@ -20,9 +20,9 @@
 //                     own tiles, no CTA-wide barrier in the loop), LayerNorm-2 + output layer +
 //                     first-max argmax inside the CTA (no cluster, no DSMEM).
 //   ls_opp_kernel     persistent, one CTA per SM, job = (opponent seat, opponent set, 128 episodes):
-//                     8 producer warps compute layer 1 + LayerNorm + ReLU for their episode rows and
-//                     write the activations, split into TF32 hi + lo parts, straight into the
-//                     128B-swizzled K-major A tiles; one thread streams the pre-split opponent fc2
+//                     8 producer warps (warp = 16-byte k chunk, lane = 4 episode rows) compute layer 1 +
+//                     LayerNorm + ReLU and write the activations, split into TF32 hi + lo parts,
+//                     straight into the 128B-swizzled K-major A tiles; one thread streams the pre-split opponent fc2
 //                     matrix with TMA; one thread issues tcgen05.mma kind::tf32 (M=128, N=256, K=8)
 //                     three times per k-step (hi.hi + lo.hi + hi.lo = "3xTF32", fp32-level accuracy)
 //                     into a double-buffered TMEM accumulator; 4 epilogue warps read it back with
@@ -550,45 +550,55 @@ __device__ __forceinline__ void op_umma(uint32_t d_tmem, uint64_t a_desc, uint64
         : "memory");
 }
 
-// One producer thread's share of an A tile: 16 of the 32 activations of k-tile kt for episode row r
-// (4 of the 8 16-byte chunks), relu(LN1(W1 x + b1)), split into TF32 hi + lo and stored K-major with
-// the 128-byte swizzle the UMMA descriptor expects (chunk c of row r at c ^ (r & 7)).
+// One producer thread's share of an A tile: 16-byte chunk c (4 activations) of k-tile kt for its FOUR
+// episode rows lane + 32 j: relu(LN1(W1 x + b1)), split into TF32 hi + lo and stored K-major with the
+// 128-byte swizzle the UMMA descriptor expects (chunk c of row r at c ^ (r & 7)).  The weight loads are
+// warp-uniform (producer warp = chunk) and serve four rows each: a shared-memory broadcast costs four
+// wavefronts per LDS.128, and with one row per thread the LSU pipe bounded the producers.  Rows of a
+// quarter warp differ in (r & 7), so the tile stores are conflict-free.
 template <int IN>
-__device__ __forceinline__ void op_produce_half(const float* __restrict__ w1a, const float (&x)[LS_OBS_PAD], float mean,
-                                                float rstd, int kt, int half, int r, unsigned char* __restrict__ a_hi,
-                                                unsigned char* __restrict__ a_lo) {
+__device__ __forceinline__ void op_produce_chunk(const float* __restrict__ w1a, const float (&x)[4][IN_GOOD],
+                                                 const float (&mean)[4], const float (&rstd)[4], int kt, int c,
+                                                 int lane, unsigned char* __restrict__ a_hi,
+                                                 unsigned char* __restrict__ a_lo) {
     const float* fc1b = w1a + H1 * IN;
     const float* ln1g = fc1b + H1;
     const float* ln1b = ln1g + H1;
+    const int k0 = kt * OP_BK + c * 4;
+    const float4 bb = *reinterpret_cast<const float4*>(fc1b + k0);
+    const float4 gg = *reinterpret_cast<const float4*>(ln1g + k0);
+    const float4 ee = *reinterpret_cast<const float4*>(ln1b + k0);
+    const float bq[4] = {bb.x, bb.y, bb.z, bb.w}, gq[4] = {gg.x, gg.y, gg.z, gg.w}, eq[4] = {ee.x, ee.y, ee.z, ee.w};
+    float hi[4][4], lo[4][4];      // [row j][k]
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-        const int c = half * 4 + cc;
-        const int k0 = kt * OP_BK + c * 4;
-        const float4 bb = *reinterpret_cast<const float4*>(fc1b + k0);
-        const float4 gg = *reinterpret_cast<const float4*>(ln1g + k0);
-        const float4 ee = *reinterpret_cast<const float4*>(ln1b + k0);
-        const float bq[4] = {bb.x, bb.y, bb.z, bb.w}, gq[4] = {gg.x, gg.y, gg.z, gg.w}, eq[4] = {ee.x, ee.y, ee.z, ee.w};
-        float hi[4], lo[4];
+    for (int qq = 0; qq < 4; ++qq) {
+        float w[IN];
+        const float2* wr = reinterpret_cast<const float2*>(w1a + (k0 + qq) * IN);
 #pragma unroll
-        for (int qq = 0; qq < 4; ++qq) {
-            const float2* wr = reinterpret_cast<const float2*>(w1a + (k0 + qq) * IN);
+        for (int i2 = 0; i2 < IN / 2; ++i2) {
+            const float2 v = wr[i2];
+            w[2 * i2] = v.x;
+            w[2 * i2 + 1] = v.y;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
             float pre = 0.f;
 #pragma unroll
-            for (int i2 = 0; i2 < IN / 2; ++i2) {
-                const float2 w = wr[i2];
-                pre = fmaf(w.x, x[2 * i2], pre);
-                pre = fmaf(w.y, x[2 * i2 + 1], pre);
-            }
+            for (int i = 0; i < IN; ++i) pre = fmaf(w[i], x[j][i], pre);
             pre += bq[qq];
-            const float h = fmaxf(fmaf((pre - mean) * rstd, gq[qq], eq[qq]), 0.f);
+            const float h = fmaxf(fmaf((pre - mean[j]) * rstd[j], gq[qq], eq[qq]), 0.f);
             // hi = h truncated to TF32 (exactly what the tensor core reads of an fp32 word); lo = h - hi is
             // exact in fp32 and is itself read truncated: relative error 2^-21, like the dropped lo.lo term
-            hi[qq] = __uint_as_float(__float_as_uint(h) & 0xffffe000u);
-            lo[qq] = h - hi[qq];
+            hi[j][qq] = __uint_as_float(__float_as_uint(h) & 0xffffe000u);
+            lo[j][qq] = h - hi[j][qq];
         }
-        const int off = (c ^ (r & 7)) << 4;
-        *reinterpret_cast<float4*>(a_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<float4*>(a_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int r = lane + 32 * j;
+        const int off = r * 128 + ((c ^ (r & 7)) << 4);
+        *reinterpret_cast<float4*>(a_hi + off) = make_float4(hi[j][0], hi[j][1], hi[j][2], hi[j][3]);
+        *reinterpret_cast<float4*>(a_lo + off) = make_float4(lo[j][0], lo[j][1], lo[j][2], lo[j][3]);
     }
 }
 
@@ -748,7 +758,7 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
     } else if (warp < 12) {
         // ===================== A producers: layer 1 + LayerNorm + ReLU -> TF32 hi/lo tiles =====
         const int pt = threadIdx.x - 128;
-        const int r = pt & 127, half = pt >> 7;       // episode row, which 4 of the 8 16-byte chunks
+        const int c = pt >> 5;                        // producer warp = 16-byte chunk (4 k) of every k-tile
         int cur_ok = -1;
         uint32_t it = 0;
         for (int job = blockIdx.x; job < p.n_jobs; job += gridDim.x) {
@@ -765,24 +775,38 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
                 asm volatile("bar.sync 1, 256;\n" ::: "memory");
                 cur_ok = okey;
             }
-            const int64_t j = (int64_t)tile * OP_BM + r;
-            const int64_t jj = j < p.PE ? j : p.PE - 1;
-            const int64_t ep = ((jj / p.E) * p.K + k) * p.E + (jj % p.E);
-            float x[LS_OBS_PAD];
-            {
+            // observations of this thread's four episode rows lane + 32 j
+            float x[4][IN_GOOD];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t jrow = (int64_t)tile * OP_BM + lane + 32 * j;
+                const int64_t jj = jrow < p.PE ? jrow : p.PE - 1;
+                const int64_t ep = ((jj / p.E) * p.K + k) * p.E + (jj % p.E);
                 const float4* src = reinterpret_cast<const float4*>(p.obs + ((int64_t)seat * p.N + ep) * LS_OBS_PAD);
                 const float4 v0 = __ldg(src), v1 = __ldg(src + 1), v2 = __ldg(src + 2);
-                x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
-                x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
-                x[8] = v2.x; x[9] = v2.y; x[10] = v2.z; x[11] = v2.w;
+                x[j][0] = v0.x; x[j][1] = v0.y; x[j][2] = v0.z; x[j][3] = v0.w;
+                x[j][4] = v1.x; x[j][5] = v1.y; x[j][6] = v1.z; x[j][7] = v1.w;
+                x[j][8] = v2.x; x[j][9] = v2.y;
             }
-            // LayerNorm-1 statistics in closed form (fp64): mean = wbar . z, var = z^T C z, z = [x; 1]
-            float mean, rstd;
+            // the job's first stage: acquire it now, its A-hi tile doubles as the exchange buffer of the
+            // LayerNorm-1 statistics (computed once per row by warps 0..3, read by all eight)
             {
+                const uint32_t st = it % OP_STAGES, use = it / OP_STAGES;
+                if (use > 0) tc_mbar_wait(bar_empty + st, (use - 1) & 1);
+            }
+            float2* xch = reinterpret_cast<float2*>(stage_mem + (size_t)(it % OP_STAGES) * OP_STAGE_BYTES);
+            if (c < 4) {
+                // closed form (fp64): mean = wbar . z, var = z^T C z, z = [x; 1], for row lane + 32 c
                 const double* S = p.l1stats + (size_t)okey * LS_L1S;
                 double z[11];
 #pragma unroll
-                for (int a = 0; a < 11; ++a) z[a] = a < in ? (double)x[a] : (a == in ? 1.0 : 0.0);
+                for (int a = 0; a < 11; ++a) {
+                    float xv = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (j == c && a < IN_GOOD) xv = x[j][a];
+                    z[a] = a < in ? (double)xv : (a == in ? 1.0 : 0.0);
+                }
                 double md = 0.0, vd = 0.0;
 #pragma unroll
                 for (int a = 0; a < 11; ++a) {
@@ -792,18 +816,29 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
                     for (int b = 0; b < 11; ++b) ra = fma(__ldg(S + 11 + a * 11 + b), z[b], ra);
                     vd = fma(ra, z[a], vd);
                 }
-                mean = (float)md;
-                const float var = (float)vd;
-                if (!isfinite(mean) || !isfinite(var)) *flag = 1;
-                rstd = 1.0f / sqrtf(var + LN_EPS);
+                const float m1 = (float)md, var = (float)vd;
+                if (!isfinite(m1) || !isfinite(var)) *flag = 1;
+                xch[lane + 32 * c] = make_float2(m1, 1.0f / sqrtf(var + LN_EPS));
             }
+            asm volatile("bar.sync 1, 256;\n" ::: "memory");
+            float mean[4], rstd[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 v = xch[lane + 32 * j];
+                mean[j] = v.x;
+                rstd[j] = v.y;
+            }
+            asm volatile("bar.sync 1, 256;\n" ::: "memory");          // exchange buffer read: the tile may be written
             for (int kt = 0; kt < OP_KT; ++kt, ++it) {
                 const uint32_t st = it % OP_STAGES, use = it / OP_STAGES;
-                if (use > 0) tc_mbar_wait(bar_empty + st, (use - 1) & 1);
-                unsigned char* a_hi = stage_mem + (size_t)st * OP_STAGE_BYTES + (size_t)r * 128;
+                if (kt > 0 && use > 0) tc_mbar_wait(bar_empty + st, (use - 1) & 1);
+                unsigned char* a_hi = stage_mem + (size_t)st * OP_STAGE_BYTES;
                 unsigned char* a_lo = a_hi + OP_A_BYTES;
-                if (in == IN_GOOD) op_produce_half<IN_GOOD>(w1a, x, mean, rstd, kt, half, r, a_hi, a_lo);
-                else op_produce_half<IN_ADV>(w1a, x, mean, rstd, kt, half, r, a_hi, a_lo);
+                if (in == IN_GOOD) {
+                    op_produce_chunk<IN_GOOD>(w1a, x, mean, rstd, kt, c, lane, a_hi, a_lo);
+                } else {
+                    op_produce_chunk<IN_ADV>(w1a, x, mean, rstd, kt, c, lane, a_hi, a_lo);
+                }
                 asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic writes -> tensor core reads
                 tc_mbar_arrive(bar_full + st);
             }
