@@ -12,7 +12,8 @@ from ctypes import (POINTER, Structure, c_char_p, c_double, c_float, c_int, c_in
                     c_int64, c_uint8, c_uint32, c_uint64, c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libcoevonet_b200.so")
+#: COEVONET_LIB selects another build of the same library (development experiments only)
+LIB_PATH = os.environ.get("COEVONET_LIB") or os.path.join(_HERE, "csrc", "libcoevonet_b200.so")
 
 CEV_OK = 0
 STATUS_NONFINITE = 1
@@ -108,14 +109,17 @@ def check(rc, what=""):
 _handles = {}
 
 
-def handle(device_index):
-    """Per-device library handle (created on first use)."""
-    h = _handles.get(device_index)
+def handle(device_index, stream=0):
+    """Library handle of (device, stream), created on first use.  A handle owns the scratch
+    workspaces of the rollout kernels, so work issued concurrently on several CUDA streams needs
+    one handle per stream (``stream`` = the raw ``cudaStream_t`` value; 0 = the default handle)."""
+    key = (int(device_index), int(stream or 0))
+    h = _handles.get(key)
     if h is None:
         lib = load()
         hp = c_void_p()
         check(lib.cev_create(int(device_index), ctypes.byref(hp)), "cev_create")
-        h = _handles[device_index] = hp
+        h = _handles[key] = hp
     return h
 
 

@@ -834,11 +834,13 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
                 if (kt > 0 && use > 0) tc_mbar_wait(bar_empty + st, (use - 1) & 1);
                 unsigned char* a_hi = stage_mem + (size_t)st * OP_STAGE_BYTES;
                 unsigned char* a_lo = a_hi + OP_A_BYTES;
+#if !(defined(CEV_EXP) && (CEV_EXP & 1))      // development experiment: bit 0 = producers write nothing
                 if (in == IN_GOOD) {
                     op_produce_chunk<IN_GOOD>(w1a, x, mean, rstd, kt, c, lane, a_hi, a_lo);
                 } else {
                     op_produce_chunk<IN_ADV>(w1a, x, mean, rstd, kt, c, lane, a_hi, a_lo);
                 }
+#endif
                 asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic writes -> tensor core reads
                 tc_mbar_arrive(bar_full + st);
             }
@@ -853,9 +855,14 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
                     const uint32_t st = it % OP_STAGES, use = it / OP_STAGES;
                     if (use > 0) tc_mbar_wait(bar_empty + st, (use - 1) & 1);
                     unsigned char* b_hi = stage_mem + (size_t)st * OP_STAGE_BYTES + 2 * OP_A_BYTES;
+#if defined(CEV_EXP) && (CEV_EXP & 2)         // development experiment: bit 1 = no opponent matrix stream
+                    tc_mbar_arrive(bar_full + st);
+                    (void)b_hi;
+#else
                     tc_mbar_expect_tx(bar_full + st, 2 * OP_B_BYTES);
                     tma_load_2d(b_hi, &map_b, bar_full + st, kt * OP_BK, (okey * 2 + 0) * H2);
                     tma_load_2d(b_hi + OP_B_BYTES, &map_b, bar_full + st, kt * OP_BK, (okey * 2 + 1) * H2);
+#endif
                 }
             }
         }

@@ -109,6 +109,11 @@ class _EngineBase:
         #: bench hook: when a list, (start, stop) CUDA events are recorded around every
         #: population K1 launch on the launching stream
         self.k1_events = None
+        #: evaluate the three roles of a generation on three CUDA streams (they are independent: every
+        #: member plays the OTHER roles' base policies of the previous generation), so one role's kernels
+        #: fill the partial waves and launch gaps of another's
+        self.overlap_roles = bool(getattr(args, "overlap_roles", True)) and self.device.type == "cuda"
+        self._role_streams = None
 
     # initial states of `n_rows` x K x E episodes for the rows [row0, row0+n_local) of a
     # P-row evaluation; in reference mode every rank draws the whole block to keep the
@@ -318,7 +323,7 @@ class ESEngine(_EngineBase):
         ref_init = init_by_role
         if ref_init is None and self.init_mode == "reference":
             ref_init = self._reference_initial_states()
-        for role in ROLES:
+        def one_role(role):
             in_dim = layout.OBS_DIM[role]
             self.k.es_perturb(self.theta[role], in_dim, self.sigma(role), self.seed, role, self.gen,
                               self.shard.row0, self.shard.n_local, out=self.members[role])
@@ -339,6 +344,20 @@ class ESEngine(_EngineBase):
                 self.k1_events.append((e0, e1))
             slot = self._role_slot(out, role, limit)                  # [n_local, 1, E]
             self.rewards[role] = slot.mean(dim=(1, 2)).contiguous()
+
+        if self.overlap_roles and self.k1_events is None:
+            if self._role_streams is None:
+                self._role_streams = [torch.cuda.Stream(device=self.device) for _ in ROLES]
+            main = torch.cuda.current_stream(self.device)
+            for role, st in zip(ROLES, self._role_streams):
+                st.wait_stream(main)
+                with torch.cuda.stream(st):
+                    one_role(role)
+            for st in self._role_streams:
+                main.wait_stream(st)
+        else:
+            for role in ROLES:
+                one_role(role)
 
     def update(self):
         """compute_weight_update + apply (evolutionary_strategy.py:120-148,255-265)."""

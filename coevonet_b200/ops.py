@@ -45,6 +45,11 @@ def _stream(dev):
     return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
+def _h(dev):
+    """The library handle of the device and the CURRENT stream (one scratch workspace per stream)."""
+    return handle(dev.index, torch.cuda.current_stream(dev).cuda_stream)
+
+
 def _need_cuda(*tensors):
     dev = None
     for t in tensors:
@@ -142,7 +147,7 @@ def mpe_rollout(member_role, members, opp_a, opp_b, init, *, n_cycles=MAX_CYCLES
     cfg = RolloutCfg(int(n_cycles), int(bool(pos_first)), int(variant), 0)
     _, n_launch = rollout_plan(dev.index, P, K, E, n_cycles, variant)
     check(_call("cev_mpe_rollout_f32",
-        handle(dev.index), seat, _ptr(members), P, members.stride(0),
+        _h(dev), seat, _ptr(members), P, members.stride(0),
         _ptr(opp_a), opp_a.stride(0), _ptr(opp_b), opp_b.stride(0), K,
         _ptr(init), int(bool(init_shared)), E, ctypes.byref(cfg), _ptr(out), _ptr(status),
         _stream(dev), launches=n_launch), "cev_mpe_rollout_f32")
@@ -160,7 +165,7 @@ def mpe_rollout_indexed(w_adv, w_a0, w_a1, idx, init, *, n_cycles=MAX_CYCLES, po
         out = torch.empty((N, _lib.ROLLOUT_OUT_DIM), dtype=torch.float64, device=dev)
     cfg = RolloutCfg(int(n_cycles), int(bool(pos_first)), 1, 0)
     check(_call("cev_mpe_rollout_indexed_f32", 
-        handle(dev.index), _ptr(w_adv), w_adv.stride(0), _ptr(w_a0), w_a0.stride(0),
+        _h(dev), _ptr(w_adv), w_adv.stride(0), _ptr(w_a0), w_a0.stride(0),
         _ptr(w_a1), w_a1.stride(0), _ptr(idx), _ptr(init), N, ctypes.byref(cfg), _ptr(out),
         _ptr(status), _stream(dev)), "cev_mpe_rollout_indexed_f32")
     return out
@@ -177,7 +182,7 @@ def fc_forward(rows, in_dim, obs, idx=None, *, status=None):
         raise _lib.CevError("fc_forward: idx must be int32")
     logits = torch.empty((N, layout.NACT), dtype=torch.float32, device=dev)
     actions = torch.empty(N, dtype=torch.int32, device=dev)
-    check(_call("cev_fc_forward_f32", handle(dev.index), _ptr(rows), rows.stride(0), int(in_dim), _ptr(idx),
+    check(_call("cev_fc_forward_f32", _h(dev), _ptr(rows), rows.stride(0), int(in_dim), _ptr(idx),
                                     _ptr(obs), N, _ptr(logits), _ptr(actions), _ptr(status), _stream(dev)),
           "cev_fc_forward_f32")
     return logits, actions
@@ -191,7 +196,7 @@ def ga_repopulate(elites, dim, sigma, seed, role, gen, row0, n_rows, *, out=None
         out = torch.empty((n_rows, pitch), dtype=torch.float32, device=dev)
     role_id = layout.ROLE_ID[role] if isinstance(role, str) else int(role)
     check(_call("cev_ga_repopulate_f32", 
-        handle(dev.index), _ptr(elites), elites.shape[0], int(dim), pitch, float(sigma),
+        _h(dev), _ptr(elites), elites.shape[0], int(dim), pitch, float(sigma),
         int(seed), role_id, int(gen), int(row0), int(n_rows), _ptr(out), _ptr(noise_out),
         _stream(dev)), "cev_ga_repopulate_f32")
     return out
@@ -203,7 +208,7 @@ def gather_rows(src, idx, *, out=None):
         raise _lib.CevError("gather_rows: idx must be int64")
     if out is None:
         out = torch.empty((idx.shape[0], src.stride(0)), dtype=torch.float32, device=dev)
-    check(_call("cev_gather_rows_f32", handle(dev.index), _ptr(src), src.stride(0), _ptr(idx),
+    check(_call("cev_gather_rows_f32", _h(dev), _ptr(src), src.stride(0), _ptr(idx),
                                      idx.shape[0], _ptr(out), _stream(dev)), "cev_gather_rows_f32")
     return out
 
@@ -214,7 +219,7 @@ def select_topk(fitness, k):
     if fitness.dtype != torch.float64 or fitness.dim() != 1:
         raise _lib.CevError("select_topk: fitness must be float64 [P]")
     idx = torch.empty(k, dtype=torch.int64, device=dev)
-    check(_call("cev_select_topk_f64", handle(dev.index), _ptr(fitness), fitness.shape[0], int(k),
+    check(_call("cev_select_topk_f64", _h(dev), _ptr(fitness), fitness.shape[0], int(k),
                                      _ptr(idx), _stream(dev)), "cev_select_topk_f64")
     return idx
 
@@ -229,7 +234,7 @@ def es_perturb(theta, in_dim, sigma, seed, role, gen, row0, n_rows, *, out=None,
         out = torch.empty((n_rows, pitch), dtype=torch.float32, device=dev)
     role_id = layout.ROLE_ID[role] if isinstance(role, str) else int(role)
     check(_call("cev_es_perturb_f32", 
-        handle(dev.index), _ptr(theta), int(in_dim), float(sigma), int(seed), role_id, int(gen),
+        _h(dev), _ptr(theta), int(in_dim), float(sigma), int(seed), role_id, int(gen),
         int(row0), int(n_rows), pitch, _ptr(out), _ptr(noise_out), _stream(dev)), "cev_es_perturb_f32")
     return out
 
@@ -245,7 +250,7 @@ def es_update(fitness, in_dim, sigma, lr, n_total, seed, role, gen, row0, *, out
         out = torch.empty(pitch, dtype=torch.float32, device=dev)
     role_id = layout.ROLE_ID[role] if isinstance(role, str) else int(role)
     check(_call("cev_es_update_f32", 
-        handle(dev.index), _ptr(fitness), int(in_dim), float(sigma), float(lr), int(n_total),
+        _h(dev), _ptr(fitness), int(in_dim), float(sigma), float(lr), int(n_total),
         int(seed), role_id, int(gen), int(row0), fitness.shape[0], _ptr(out), _stream(dev)),
         "cev_es_update_f32")
     return out
@@ -253,7 +258,7 @@ def es_update(fitness, in_dim, sigma, lr, n_total, seed, role, gen, row0, *, out
 
 def axpy(a, x, y):
     dev = _need_cuda(x, y)
-    check(_call("cev_axpy_f32", handle(dev.index), float(a), _ptr(x), _ptr(y), min(x.numel(), y.numel()),
+    check(_call("cev_axpy_f32", _h(dev), float(a), _ptr(x), _ptr(y), min(x.numel(), y.numel()),
                               _stream(dev)), "cev_axpy_f32")
     return y
 
@@ -263,7 +268,7 @@ def diversity_dist(pop, ref, in_dim, *, out=None):
     dev = _need_cuda(pop, ref, out)
     if out is None:
         out = torch.empty(pop.shape[0], dtype=torch.float32, device=dev)
-    check(_call("cev_diversity_dist_f32", handle(dev.index), _ptr(pop), pop.shape[0], pop.stride(0),
+    check(_call("cev_diversity_dist_f32", _h(dev), _ptr(pop), pop.shape[0], pop.stride(0),
                                         _ptr(ref), int(in_dim), _ptr(out), _stream(dev)),
           "cev_diversity_dist_f32")
     return out
@@ -285,7 +290,7 @@ def deepqn_forward(members, frames, c_in, n_actions):
         raise _lib.CevError("deepqn_forward: frames must be uint8 [P,B,C,84,84]")
     logits = torch.empty((P, B, n_actions), dtype=torch.float32, device=dev)
     actions = torch.empty((P, B), dtype=torch.int32, device=dev)
-    check(_call("cev_deepqn_forward", handle(dev.index), _ptr(members), P, members.stride(0),
+    check(_call("cev_deepqn_forward", _h(dev), _ptr(members), P, members.stride(0),
                                     _ptr(frames), B, int(c_in), int(n_actions), _ptr(logits),
                                     _ptr(actions), _stream(dev)), "cev_deepqn_forward")
     return logits, actions
@@ -299,7 +304,7 @@ def fc_init(in_dim, seed, role, row0, n_rows, device, *, out=None):
         out = torch.empty((n_rows, pitch), dtype=torch.float32, device=device)
     dev = _need_cuda(out)
     role_id = layout.ROLE_ID[role] if isinstance(role, str) else int(role)
-    check(_call("cev_fc_init_f32", handle(dev.index), int(in_dim), int(seed), role_id, int(row0), int(n_rows),
+    check(_call("cev_fc_init_f32", _h(dev), int(in_dim), int(seed), role_id, int(row0), int(n_rows),
                 pitch, _ptr(out), _stream(dev)), "cev_fc_init_f32")
     return out
 
@@ -309,7 +314,7 @@ def init_states(seed, stream_id, n, device, rec0=0):
     records rec0 .. rec0+n-1 of Philox stream ``stream_id``."""
     out = torch.empty((n, _lib.INIT_STATE_DIM), dtype=torch.float64, device=device)
     dev = out.device
-    check(_call("cev_init_states_f64", handle(dev.index), int(seed), int(stream_id), int(rec0), n, _ptr(out),
+    check(_call("cev_init_states_f64", _h(dev), int(seed), int(stream_id), int(rec0), n, _ptr(out),
                                      _stream(dev)), "cev_init_states_f64")
     return out
 
@@ -319,7 +324,7 @@ def random_frames(seed, shape, device):
     if out.numel() % 16:
         raise _lib.CevError("random_frames: byte count must be a multiple of 16")
     dev = out.device
-    check(_call("cev_random_frames_u8", handle(dev.index), int(seed), out.numel(), _ptr(out),
+    check(_call("cev_random_frames_u8", _h(dev), int(seed), out.numel(), _ptr(out),
                                       _stream(dev)), "cev_random_frames_u8")
     return out
 
@@ -327,7 +332,7 @@ def random_frames(seed, shape, device):
 def philox_words(seed, kind, role, gen, member0, n_members, n4, device):
     out = torch.empty((n_members, n4, 4), dtype=torch.int32, device=device)
     dev = out.device
-    check(_call("cev_philox_words", handle(dev.index), int(seed), int(kind), int(role), int(gen),
+    check(_call("cev_philox_words", _h(dev), int(seed), int(kind), int(role), int(gen),
                                   int(member0), int(n_members), int(n4), _ptr(out), _stream(dev)),
           "cev_philox_words")
     return out
@@ -337,6 +342,6 @@ def fp32_peak(device, mode=1):
     """Measured FP32 FMA-pipe peak in TFLOP/s (mode 0 scalar FFMA, 1 packed FFMA2)."""
     dev = torch.device(device)
     val = ctypes.c_double()
-    check(_call("cev_fp32_peak", handle(dev.index), int(mode), ctypes.byref(val), _stream(dev)),
+    check(_call("cev_fp32_peak", _h(dev), int(mode), ctypes.byref(val), _stream(dev)),
           "cev_fp32_peak")
     return val.value
