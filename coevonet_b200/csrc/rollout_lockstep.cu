@@ -229,33 +229,39 @@ __global__ void __launch_bounds__(256) ls_split_w2_kernel(const LsPrepParams p) 
 // wbar[j] = mean over the 512 rows of column j of [W1 | b1]; C[a][b] = row covariance (biased).
 // LayerNorm-1 of y = W1 x + b1:  mean(y) = wbar . z,  var(y) = z^T C z  with z = [x; 1]
 // (MPE/fcnetwork.py:44: nn.LayerNorm(512), biased variance).
-__global__ void __launch_bounds__(128) ls_l1stats_kernel(const LsPrepParams p) {
+__global__ void __launch_bounds__(512) ls_l1stats_kernel(const LsPrepParams p) {
     const int oi = blockIdx.x / p.K, k = blockIdx.x % p.K;
     const int in = seat_in_dim(p.seat[oi]), d = in + 1;
     const float* row = p.opp[oi] + (int64_t)k * p.opp_pitch[oi];
     const float* w1 = row;
     const float* b1 = row + H1 * in;
+    __shared__ float cols[11][H1];          // [W1 | b1] transposed: column a of all 512 rows
     __shared__ double wbar[11];
-    const int t = threadIdx.x;
-    if (t < 11) {
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int i = t; i < H1 * in; i += 512) cols[i % in][i / in] = w1[i];
+    cols[in][t] = b1[t];
+    __syncthreads();
+    for (int a = warp; a < 11; a += 16) {
         double s = 0.0;
-        if (t < d)
-            for (int r = 0; r < H1; ++r) s += (double)(t < in ? w1[r * in + t] : b1[r]);
-        wbar[t] = s / H1;
+        if (a < d)
+            for (int r = lane; r < H1; r += 32) s += (double)cols[a][r];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) wbar[a] = s / H1;
     }
     __syncthreads();
     double* out = p.l1stats + (size_t)blockIdx.x * LS_L1S;
     if (t < 11) out[t] = wbar[t];
-    if (t < 121) {
-        const int a = t / 11, b = t % 11;
+    for (int pr = warp; pr < 121; pr += 16) {
+        const int a = pr / 11, b = pr % 11;
         double s = 0.0;
-        if (a < d && b < d)
-            for (int r = 0; r < H1; ++r) {
-                const double va = (double)(a < in ? w1[r * in + a] : b1[r]) - wbar[a];
-                const double vb = (double)(b < in ? w1[r * in + b] : b1[r]) - wbar[b];
-                s += va * vb;
-            }
-        out[11 + t] = s / H1;
+        if (a < d && b < d) {
+            const double ma = wbar[a], mb = wbar[b];
+            for (int r = lane; r < H1; r += 32) s += ((double)cols[a][r] - ma) * ((double)cols[b][r] - mb);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) out[11 + pr] = s / H1;
     }
 }
 
@@ -952,7 +958,7 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
     pp.w2split = b.w2split;
     pp.l1stats = b.l1stats;
     ls_split_w2_kernel<<<dim3(32, 2 * p.K), 256, 0, stream>>>(pp);
-    ls_l1stats_kernel<<<2 * p.K, 128, 0, stream>>>(pp);
+    ls_l1stats_kernel<<<2 * p.K, 512, 0, stream>>>(pp);
 
     // ---- tensor maps ---------------------------------------------------------------------------
     CUtensorMap map_w2, map_b;
