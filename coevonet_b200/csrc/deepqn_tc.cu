@@ -191,260 +191,6 @@ deepqn_fc_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 }
 
 
-// ---------------------------------------------------------------------------
-// Convolutions as grouped GEMMs on tcgen05 (implicit GEMM through an explicit,
-// L2-resident im2col scratch):   Y_m[R, N] = X_m[R, K] . W_m[N, K]^T + bias_m
-//   conv1: R = 400*B, K = 64*C, N = 32      conv2: R = 81*B, K = 512, N = 64
-//   conv3: R = 49*B,  K = 576,  N = 64
-// conv weights [cout][cin*kh*kw] are already N x K, K-major.  Same warp roles and
-// pipeline as the fc kernel; work item = (member, 128-row tile).
-// ---------------------------------------------------------------------------
-constexpr int CG_STAGES = 6;
-
-struct ConvGemmParams {
-    const float* members;     // chunk base (row 0 = first member of the chunk)
-    int64_t pitch;
-    int n_members, R, n_kt, bias_off;
-    float* y;                 // [n_members * R, BN]
-};
-
-template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-                    const ConvGemmParams p) {
-    constexpr uint32_t B_BYTES = BN * TC_BK * 4;
-    constexpr uint32_t STAGE_B = TC_A_BYTES + B_BYTES;             // multiple of 1024 for BN = 32, 64
-    constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;      // 64 / 128
-    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                               ((uint32_t)(TC_BM >> 4) << 24);
-    extern __shared__ unsigned char tc_raw[];
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char* stage_mem = base;
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(base + (size_t)CG_STAGES * STAGE_B);
-    uint64_t* bar_empty = bar_full + CG_STAGES;
-    uint64_t* bar_tfull = bar_empty + CG_STAGES;
-    uint64_t* bar_tempty = bar_tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_rt = (p.R + TC_BM - 1) / TC_BM;
-    const int n_items = p.n_members * n_rt;
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < CG_STAGES; ++i) {
-            tc_mbar_init(bar_full + i, 1);
-            tc_mbar_init(bar_empty + i, 1);
-        }
-        for (int i = 0; i < 2; ++i) {
-            tc_mbar_init(bar_tfull + i, 1);
-            tc_mbar_init(bar_tempty + i, 4);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tc_smem_u32(tmem_slot)),
-                     "r"(TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int m = item / n_rt, rt = item % n_rt;
-                for (int kt = 0; kt < p.n_kt; ++kt, ++it) {
-                    const uint32_t st = it % CG_STAGES, use = it / CG_STAGES;
-                    if (use > 0) tc_mbar_wait(bar_empty + st, (use - 1) & 1);
-                    unsigned char* a = stage_mem + (size_t)st * STAGE_B;
-                    tc_mbar_expect_tx(bar_full + st, STAGE_B);
-                    tma_load_2d(a, &map_x, bar_full + st, kt * TC_BK, m * p.R + rt * TC_BM);
-                    tma_load_3d(a + TC_A_BYTES, &map_w, bar_full + st, kt * TC_BK, 0, m);
-                }
-            }
-        }
-    } else if (warp == 1) {
-        uint32_t it = 0, pass = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++pass) {
-            const uint32_t as = pass & 1, ause = pass >> 1;
-            if (ause > 0) tc_mbar_wait(bar_tempty + as, (ause - 1) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            const uint32_t d_tmem = tmem_base + as * BN;
-            for (int kt = 0; kt < p.n_kt; ++kt, ++it) {
-                const uint32_t st = it % CG_STAGES, use = it / CG_STAGES;
-                tc_mbar_wait(bar_full + st, use & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                if (lane == 0) {
-                    const uint32_t a_addr = tc_smem_u32(stage_mem + (size_t)st * STAGE_B);
-                    const uint64_t a_desc = umma_desc_sw128(a_addr);
-                    const uint64_t b_desc = umma_desc_sw128(a_addr + TC_A_BYTES);
-#pragma unroll
-                    for (int k = 0; k < TC_BK / 8; ++k) {
-                        const uint32_t acc = (kt | k) ? 1u : 0u;
-                        asm volatile(
-                            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-                            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
-                            "l"(a_desc + (uint64_t)(k * 2)), "l"(b_desc + (uint64_t)(k * 2)), "r"(IDESC), "r"(acc)
-                            : "memory");
-                    }
-                    umma_commit(bar_empty + st);
-                    if (kt == p.n_kt - 1) umma_commit(bar_tfull + as);
-                }
-                __syncwarp();
-            }
-        }
-    } else {
-        const int q = warp & 3;
-        const int row = q * 32 + lane;
-        uint32_t pass = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++pass) {
-            const int m = item / n_rt, rt = item % n_rt;
-            const float* bias = p.members + (int64_t)m * p.pitch + p.bias_off;
-            const int r = rt * TC_BM + row;
-            const uint32_t as = pass & 1, ause = pass >> 1;
-            tc_mbar_wait(bar_tfull + as, ause & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
-#pragma unroll
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(taddr + c0, v);
-                if (r < p.R) {
-                    float4* dst = reinterpret_cast<float4*>(p.y + ((int64_t)m * p.R + r) * BN + c0);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        dst[j] = make_float4(__uint_as_float(v[4 * j]) + __ldg(bias + c0 + 4 * j),
-                                             __uint_as_float(v[4 * j + 1]) + __ldg(bias + c0 + 4 * j + 1),
-                                             __uint_as_float(v[4 * j + 2]) + __ldg(bias + c0 + 4 * j + 2),
-                                             __uint_as_float(v[4 * j + 3]) + __ldg(bias + c0 + 4 * j + 3));
-                }
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-            __syncwarp();
-            if (lane == 0) tc_mbar_arrive(bar_tempty + as);
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-    __syncthreads();
-    if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
-    }
-}
-
-// ---------------------------------------------------------------------------
-// im2col of the input frames: X1[(f*400 + oy*20 + ox)][ci*64 + ky*8 + kx] = frame[ci][4oy+ky][4ox+kx] / 255
-// one CTA per frame, frame staged as u8 in shared memory, i/255 through a 256-entry table
-// (bit-exact with the reference's fp32 division).
-// ---------------------------------------------------------------------------
-template <int CIN>
-__global__ void __launch_bounds__(256) im2col_frames_kernel(const uint8_t* __restrict__ frames, int64_t n_frames,
-                                                            float* __restrict__ x1) {
-    __shared__ __align__(16) uint8_t fr[CIN * 7056];
-    __shared__ float lut[256];
-    constexpr int K = CIN * 64;
-    for (int64_t f = blockIdx.x; f < n_frames; f += gridDim.x) {
-        __syncthreads();
-        const uint8_t* src = frames + f * CIN * 7056;
-        for (int i = threadIdx.x; i < CIN * 7056 / 16; i += 256)
-            reinterpret_cast<uint4*>(fr)[i] = __ldg(reinterpret_cast<const uint4*>(src) + i);
-        lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);
-        __syncthreads();
-        float* dst = x1 + f * 400 * K;
-        for (int i = threadIdx.x; i < 400 * K / 4; i += 256) {
-            const int e = i * 4, pos = e / K, col = e % K;
-            const int ci = col >> 6, ky = (col >> 3) & 7, kx = col & 7;      // kx in {0, 4}
-            const int oy = pos / 20, ox = pos % 20;
-            const uint8_t* s = fr + ci * 7056 + (oy * 4 + ky) * 84 + ox * 4 + kx;
-            reinterpret_cast<float4*>(dst)[i] = make_float4(lut[s[0]], lut[s[1]], lut[s[2]], lut[s[3]]);
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------
-// Per-frame train-mode BatchNorm + ReLU on a GEMM output Y[(f*NPOS + pos)][COUT], then
-// either the next layer's im2col matrix (MODE 0) or torch's flatten order (MODE 1).
-// One CTA per frame.  Two-pass statistics per channel (biased variance, eps 1e-5).
-// ---------------------------------------------------------------------------
-template <int COUT, int HIN, int KS, int STRIDE, int HOUT, int MODE>
-__global__ void __launch_bounds__(256) bn_relu_rearrange_kernel(const float* __restrict__ y, int64_t n_frames, int B,
-                                                                const float* __restrict__ members, int64_t pitch,
-                                                                int g_off, int b_off, float* __restrict__ out) {
-    constexpr int NPOS = HIN * HIN;
-    constexpr int LD = NPOS + 1;                       // padded: conflict-free transposed access
-    extern __shared__ __align__(16) float bn_smem[];
-    float* yt = bn_smem;                               // [COUT][LD]  (transposed, normalised in place)
-    float* red = yt + COUT * LD;                       // [8][COUT] partial sums
-    float* stat = red + 8 * COUT;                      // [COUT] mean, [COUT] rstd
-    const int t = threadIdx.x;
-    for (int64_t f = blockIdx.x; f < n_frames; f += gridDim.x) {
-        const float* W = members + (f / B) * pitch;
-        const float* src = y + f * NPOS * COUT;
-        __syncthreads();
-        for (int i = t; i < NPOS * COUT; i += 256) {
-            const int pos = i / COUT, c = i % COUT;
-            yt[c * LD + pos] = src[i];
-        }
-        __syncthreads();
-        // mean: thread (c = t % COUT, g = t / COUT) sums positions g, g + G, ...
-        constexpr int G = 256 / COUT;
-        {
-            const int c = t % COUT, g = t / COUT;
-            float s = 0.f;
-            for (int pos = g; pos < NPOS; pos += G) s += yt[c * LD + pos];
-            red[g * COUT + c] = s;
-        }
-        __syncthreads();
-        if (t < COUT) {
-            float s = 0.f;
-            for (int g = 0; g < G; ++g) s += red[g * COUT + t];
-            stat[t] = s * (1.0f / NPOS);
-        }
-        __syncthreads();
-        {
-            const int c = t % COUT, g = t / COUT;
-            const float mean = stat[c];
-            float q = 0.f;
-            for (int pos = g; pos < NPOS; pos += G) {
-                const float d = yt[c * LD + pos] - mean;
-                q = fmaf(d, d, q);
-            }
-            red[g * COUT + c] = q;
-        }
-        __syncthreads();
-        if (t < COUT) {
-            float q = 0.f;
-            for (int g = 0; g < G; ++g) q += red[g * COUT + t];
-            stat[COUT + t] = 1.0f / sqrtf(q * (1.0f / NPOS) + 1e-5f);
-        }
-        __syncthreads();
-        for (int i = t; i < NPOS * COUT; i += 256) {
-            const int c = i / NPOS, pos = i % NPOS;
-            const float v = (yt[c * LD + pos] - stat[c]) * stat[COUT + c];
-            yt[c * LD + pos] = fmaxf(fmaf(v, __ldg(W + g_off + c), __ldg(W + b_off + c)), 0.f);
-        }
-        __syncthreads();
-        if (MODE == 1) {
-            // flatten like x.reshape(B, -1) of [C, H, W]: index c*NPOS + pos
-            float* dst = out + f * COUT * NPOS;
-            for (int i = t; i < COUT * NPOS; i += 256) dst[i] = yt[(i / NPOS) * LD + (i % NPOS)];
-        } else {
-            // next layer's im2col: X[(f*HOUT*HOUT + oy*HOUT + ox)][ci*KS*KS + ky*KS + kx]
-            constexpr int KN = COUT * KS * KS;
-            float* dst = out + f * HOUT * HOUT * KN;
-            for (int i = t; i < HOUT * HOUT * KN; i += 256) {
-                const int p2 = i / KN, col = i % KN;
-                const int ci = col / (KS * KS), ky = (col / KS) % KS, kx = col % KS;
-                const int oy = p2 / HOUT, ox = p2 % HOUT;
-                dst[i] = yt[ci * LD + (oy * STRIDE + ky) * HIN + ox * STRIDE + kx];
-            }
-        }
-    }
-}
-
 // fc1 + output layer + argmax for all members on the tensor cores.
 // act3: fp32 [P*B, 3136] (conv3 output, post BN + ReLU, flattened like torch's reshape).
 int launch_deepqn_fc_tc(cev_handle* h, const float* members, int64_t pitch, int P, int B, int n_act, int f1w_off,

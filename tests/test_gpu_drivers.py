@@ -164,3 +164,40 @@ def test_play_game_and_helpers_dropin():
                                         population_weights=[after.numpy()[pidx]] * 3)
     want_upd = (0.1 / (3 * args.mutation_power_agent_0)) * noise.astype(np.float32) * 6.0 / (1 + div)
     np.testing.assert_allclose(upd, want_upd, rtol=1e-4, atol=1e-7)
+
+
+def test_es_role_overlap_and_kernel_timing_do_not_change_results():
+    """The three roles of an ES generation on three CUDA streams (one library handle each) must give
+    bit-identical rewards and base rows to the serial order; the kernel-timing hook reports one
+    member and one opponent kernel per world step of every lockstep rollout."""
+    import types
+    from coevonet_b200 import engine, layout, ops
+    from coevonet_b200.MPE.fcnetwork import FCNetwork
+
+    def make(overlap):
+        args = types.SimpleNamespace(
+            algorithm="ES", generations=1, population=192, hof_size=1, game="simple_adversary_v3",
+            mutation_power_agent_0=0.05, mutation_power_agent_1=0.05, mutation_power_adversary=0.05,
+            learning_rate=0.1, max_timesteps_per_episode=400, max_evaluation_steps=400, elites_number=2,
+            adaptive=False, max_mutation_power=0.5, min_mutation_power=0.001, fitness_sharing=False,
+            early_stopping=False, patience=300, min_delta=0.1, debug=False, precision="float32",
+            save=False, envs_per_member=16, reference_compat=True, init_states="device",
+            seed=1870300, plots=False, record_history=False, overlap_roles=overlap)
+        torch.manual_seed(0)
+        theta = {r: FCNetwork(layout.OBS_DIM[r], 5, "float32").flat_row() for r in engine.ROLES}
+        return engine.ESEngine(args, torch.device("cuda", 0), theta)
+
+    a, b = make(True), make(False)
+    assert ops.rollout_plan(0, 192, 1, 16)[0] == 3
+    ops.kernel_timing_enable(0, True)
+    for _ in range(2):
+        a.step()
+        b.step()
+    torch.cuda.synchronize()
+    ms, n = ops.kernel_timing_read(0, 0)
+    ms_o, n_o = ops.kernel_timing_read(0, 1)
+    ops.kernel_timing_enable(0, False)
+    assert n == n_o == 2 * 3 * 25 and ms > 0 and ms_o > 0      # engine b (default stream handle): 2 steps x 3 roles
+    for r in engine.ROLES:
+        assert torch.equal(a.rewards[r], b.rewards[r])
+        assert torch.equal(a.theta[r], b.theta[r])
