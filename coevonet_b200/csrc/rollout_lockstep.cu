@@ -14,11 +14,11 @@
 // GEMM and belongs on the tensor cores; only the member's own forward (unique weights per
 // member) stays on the FP32 pipe.  Per world step:
 //
-//   ls_member_kernel  one CTA per (member, 16 episodes): layer 1 + LayerNorm on CUDA cores, fc2 with
-//                     packed FFMA2 from 8 KB TMA tensor tiles ([64 rows x 32 k], 128B swizzle) of the
-//                     member's own row streamed from HBM/L2 (16 slots, each warp double-buffers its
-//                     own tiles, no CTA-wide barrier in the loop), LayerNorm-2 + output layer +
-//                     first-max argmax inside the CTA (no cluster, no DSMEM).
+//   ls_member_kernel  one 4-warp CTA per (member, 16 episodes), two CTAs per SM: layer 1 + LayerNorm on CUDA
+//                     cores, fc2 with packed FFMA2 (8 rows x 8 envs of accumulators per lane) from 8 KB TMA
+//                     tensor tiles ([128 rows x 16 k], 64B swizzle) of the member's own row streamed from
+//                     HBM (8 slots, each warp double-buffers its own tiles, no CTA-wide barrier in the
+//                     loop), LayerNorm-2 + output layer + first-max argmax inside the CTA.
 //   ls_opp_kernel     persistent, one CTA per SM, job = (opponent seat, opponent set, 128 episodes):
 //                     8 producer warps (warp = 16-byte k chunk, lane = 4 episode rows) compute layer 1 +
 //                     LayerNorm + ReLU and write the activations, split into TF32 hi + lo parts,
@@ -269,25 +269,30 @@ __global__ void __launch_bounds__(512) ls_l1stats_kernel(const LsPrepParams p) {
 // member forward (FP32 pipe)
 // ---------------------------------------------------------------------------------------------
 constexpr int LS_BT = 16;                         // episodes per CTA
+constexpr int LS_MT = 128;                        // threads per member CTA (4 warps)
+constexpr int LS_MW = LS_MT / 32;
 constexpr int LS_TILE_K = 16;                     // k per tile
-constexpr int LS_TILE_BYTES = 64 * LS_TILE_K * 4; // [64 rows x 16 k] fp32 = 4 KB, 64B-swizzled
-constexpr int LS_NSLOT = 16;
-constexpr int LS_TPW = (H1 / LS_TILE_K) / 2;      // 16 tiles per warp: one row quarter, one k half
+constexpr int LS_TILE_ROWS = 128;
+constexpr int LS_TILE_BYTES = LS_TILE_ROWS * LS_TILE_K * 4;   // [128 rows x 16 k] fp32 = 8 KB, 64B-swizzled
+constexpr int LS_NSLOT = 8;
+constexpr int LS_TPW = (H1 / LS_TILE_K) / 2;      // 16 tiles per warp: one row half, one k half
 constexpr int LS_TAIL_FLOATS = 2056;              // fc2.b | ln2.g | ln2.b | out.W | out.b (+3 pad), contiguous in the row
 constexpr int LS_W1A_FLOATS = H1 * IN_GOOD + 3 * H1;
 
-// Two CTAs per SM (113 KB each): while one CTA is in its latency-bound phases (layer 1, LayerNorm,
-// reductions, launch prologue) the other one keeps the FMA pipe and the HBM stream busy.  The W1
-// block is only needed by layer 1, so ring slots 8..15 alias it.
+// Two CTAs of four warps per SM (107 KB, up to 255 registers each): every lane owns an 8 rows x 8 envs
+// accumulator tile, so a 4-k step is 16 LDS.128 for 128 FFMA2 (the 8 x 4 tile of an 8-warp CTA needed 12
+// for 64 and left the LSU pipe as busy as the FMA pipe).  While one CTA is in its latency-bound phases
+// (layer 1, LayerNorm, reductions, launch prologue) the other one keeps the FMA pipe and the HBM stream
+// busy.  The W1 block is only needed by layer 1, so ring slots 4..7 alias it.
 struct LsMemberSmem {
     static constexpr size_t off_ring = 0;
-    static constexpr size_t off_w1a = off_ring + (size_t)(LS_NSLOT / 2) * LS_TILE_BYTES;   // = slots 8..15
+    static constexpr size_t off_w1a = off_ring + (size_t)(LS_NSLOT / 2) * LS_TILE_BYTES;   // = slots 4..7
     static constexpr size_t off_h1p = off_ring + (size_t)LS_NSLOT * LS_TILE_BYTES;
     static constexpr size_t off_tail = off_h1p + (size_t)H1 * LS_BT * 4;
     static constexpr size_t off_obs = off_tail + (size_t)LS_TAIL_FLOATS * 4;
     static constexpr size_t off_red1 = off_obs + (size_t)LS_BT * 12 * 4;
-    static constexpr size_t off_red = off_red1 + (size_t)2 * NW * LS_BT * 4;
-    static constexpr size_t off_flag = off_red + (size_t)7 * NW * LS_BT * 4;
+    static constexpr size_t off_red = off_red1 + (size_t)2 * LS_MW * LS_BT * 4;
+    static constexpr size_t off_flag = off_red + (size_t)7 * LS_MW * LS_BT * 4;
     static constexpr size_t off_bar = off_flag + 16;
     static constexpr size_t total = off_bar + (size_t)(LS_NSLOT + 2) * 8 + 1024 /*alignment slack*/;
 };
@@ -305,31 +310,135 @@ struct LsMemberParams {
     int32_t* status;
 };
 
-// One [64 rows x 16 k] tile of fc2 for one warp: lane = (eg = lane % 4: 4 envs, rl = lane / 4: row lane),
-// rows rl + 8 i (i < 8).  Tile rows are 64 bytes, 16-byte chunk c of row r stored at c ^ ((r >> 1) & 3)
-// (TMA SWIZZLE_64B): the 8 row lanes of a load hit 8 distinct bank groups.
+// Layer 1 + LayerNorm + ReLU for the CTA's BT episodes with LS_MT threads (the 128-thread form of
+// rollout_common.cuh's layer1): thread (ep = t % 8 env pair, g = t / 8) owns the row PAIRS g + 16 i;
+// output in the k-pair interleaved layout h1p[(k >> 1) * (2 BT) + 2 e + (k & 1)].
+template <int IN>
+__device__ __forceinline__ void ls_layer1(const float* __restrict__ w1a, const float* __restrict__ obs_seat,
+                                          float* __restrict__ h1p, float* __restrict__ red1, int* flag) {
+    constexpr int BT = LS_BT;
+    constexpr int NEP = BT / 2;             // env pairs
+    constexpr int G = LS_MT / NEP;          // 16 row-pair groups
+    constexpr int NP = (H1 / 2) / G;        // 16 row pairs per thread
+    constexpr int NV = 2 * IN / 4;          // float4 per row pair of fc1.W
+    const int t = threadIdx.x, ep = t % NEP, g = t / NEP, warp = t >> 5, lane = t & 31;
+    const float* fc1w = w1a;
+    const float* fc1b = w1a + H1 * IN;
+    const float* ln1g = fc1b + H1;
+    const float* ln1b = ln1g + H1;
+
+    float2 ob[2][IN / 2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int k = 0; k < IN / 2; ++k)
+            ob[j][k] = *reinterpret_cast<const float2*>(obs_seat + (2 * ep + j) * 12 + 2 * k);
+
+    float pre[NP][2][2];                    // [pair][row in pair][env in pair]
+    float lsum[2] = {0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        const int rp = g + G * i;
+        float w[2 * IN];
+        const float4* wp = reinterpret_cast<const float4*>(fc1w + rp * 2 * IN);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const float4 x = wp[v];
+            w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
+        }
+        const float2 bb = *reinterpret_cast<const float2*>(fc1b + 2 * rp);
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < IN / 2; ++k)
+                    acc = ffma2(make_float2(w[r * IN + 2 * k], w[r * IN + 2 * k + 1]), ob[j][k], acc);
+                pre[i][r][j] = (acc.x + acc.y) + (r ? bb.y : bb.x);
+                lsum[j] += pre[i][r][j];
+            }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        lsum[j] = group_sum<NEP>(lsum[j]);
+        if (lane < NEP) red1[warp * BT + 2 * ep + j] = lsum[j];
+    }
+    __syncthreads();
+    float mean[2], lsq[2] = {0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < LS_MW; ++w) tot += red1[w * BT + 2 * ep + j];
+        mean[j] = tot * (1.0f / H1);
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i)
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                pre[i][r][j] -= mean[j];
+                lsq[j] = fmaf(pre[i][r][j], pre[i][r][j], lsq[j]);
+            }
+    float* red1b = red1 + LS_MW * BT;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        lsq[j] = group_sum<NEP>(lsq[j]);
+        if (lane < NEP) red1b[warp * BT + 2 * ep + j] = lsq[j];
+    }
+    __syncthreads();
+    float rstd[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < LS_MW; ++w) tot += red1b[w * BT + 2 * ep + j];
+        const float var = tot * (1.0f / H1);
+        if (!isfinite(mean[j]) || !isfinite(var)) *flag = 1;
+        rstd[j] = 1.0f / sqrtf(var + LN_EPS);
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        const int rp = g + G * i;
+        const float2 gg = *reinterpret_cast<const float2*>(ln1g + 2 * rp);
+        const float2 be = *reinterpret_cast<const float2*>(ln1b + 2 * rp);
+        float4 o;
+        o.x = fmaxf(fmaf(pre[i][0][0] * rstd[0], gg.x, be.x), 0.f);
+        o.y = fmaxf(fmaf(pre[i][1][0] * rstd[0], gg.y, be.y), 0.f);
+        o.z = fmaxf(fmaf(pre[i][0][1] * rstd[1], gg.x, be.x), 0.f);
+        o.w = fmaxf(fmaf(pre[i][1][1] * rstd[1], gg.y, be.y), 0.f);
+        *reinterpret_cast<float4*>(h1p + rp * (2 * BT) + 4 * ep) = o;
+    }
+}
+
+// One [128 rows x 16 k] tile of fc2 for one warp: lane = (eg = lane & 1: 8 envs, rl = lane >> 1: row lane),
+// rows rl + 16 i (i < 8).  Tile rows are 64 bytes, 16-byte chunk c of row r stored at c ^ ((r >> 1) & 3)
+// (TMA SWIZZLE_64B): the 16 row lanes of a load read 256 bytes in the minimal two wavefronts.
 __device__ __forceinline__ void ls_fc2_tile(const float4* __restrict__ tile, const float* __restrict__ h1p, int kbase,
-                                            float2 (&acc)[8][4]) {
+                                            float2 (&acc)[8][8]) {
     const int lane = threadIdx.x & 31;
-    const int eg = lane & 3, rl = lane >> 2;
-    const int sw = (rl >> 1) & 3;
+    const int eg = lane & 1, rl = lane >> 1;
+    const int sw = (rl >> 1) & 3;                 // (r >> 1) & 3 for r = rl + 16 i
     const float4* wrow0 = tile + rl * 4;
-    const float* hbase = h1p + (kbase >> 1) * (2 * LS_BT) + eg * 8;
+    const float* hbase = h1p + (kbase >> 1) * (2 * LS_BT) + eg * 16;
 #pragma unroll
     for (int st = 0; st < LS_TILE_K / 4; ++st) {
-        float4 a[2][2];
+        // activations: two k-pairs x four env-pairs ((k even, k odd) per env)
+        float4 a[2][4];
 #pragma unroll
         for (int kp = 0; kp < 2; ++kp)
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
+            for (int j = 0; j < 4; ++j)
                 a[kp][j] = *reinterpret_cast<const float4*>(hbase + (2 * st + kp) * (2 * LS_BT) + j * 4);
         const int col = st ^ sw;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float4 w = wrow0[i * 32 + col];
+            const float4 w = wrow0[i * 64 + col];
             const float2 w0 = make_float2(w.x, w.y), w1 = make_float2(w.z, w.w);
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
+            for (int j = 0; j < 4; ++j) {
                 acc[i][2 * j] = ffma2(w0, make_float2(a[0][j].x, a[0][j].y), acc[i][2 * j]);
                 acc[i][2 * j] = ffma2(w1, make_float2(a[1][j].x, a[1][j].y), acc[i][2 * j]);
                 acc[i][2 * j + 1] = ffma2(w0, make_float2(a[0][j].z, a[0][j].w), acc[i][2 * j + 1]);
@@ -339,25 +448,25 @@ __device__ __forceinline__ void ls_fc2_tile(const float4* __restrict__ tile, con
     }
 }
 
-__global__ void __launch_bounds__(CT, 2)
+__global__ void __launch_bounds__(LS_MT, 2)
 ls_member_kernel(const __grid_constant__ CUtensorMap map_w2, const LsMemberParams p) {
     using L = LsMemberSmem;
     constexpr int BT = LS_BT;
-    constexpr int G = CT / BT;       // 16 row groups
-    constexpr int RP = H2 / G;       // 16 fc2 rows per thread after the k-split reduce
+    constexpr int G = LS_MT / BT;    // 8 row groups
+    constexpr int RP = H2 / G;       // 32 fc2 rows per thread after the k-split reduce
     // 1024-byte alignment for the swizzled TMA tiles, computed as an OFFSET into the __shared__ array so
     // the compiler keeps the shared address space (LDS/STS, not generic LD/ST)
     extern __shared__ unsigned char ls_raw[];
     unsigned char* smem = ls_raw + ((1024u - (smem_u32(ls_raw) & 1023u)) & 1023u);
     unsigned char* ring = smem + L::off_ring;
     float* h1p = reinterpret_cast<float*>(smem + L::off_h1p);        // activations, later the k-split partials
-    float* w1a = reinterpret_cast<float*>(smem + L::off_w1a);        // aliases ring slots 8..15
+    float* w1a = reinterpret_cast<float*>(smem + L::off_w1a);        // aliases ring slots 4..7
     float* tail = reinterpret_cast<float*>(smem + L::off_tail);
     float* obs = reinterpret_cast<float*>(smem + L::off_obs);
     float* red1 = reinterpret_cast<float*>(smem + L::off_red1);
-    float* redA = reinterpret_cast<float*>(smem + L::off_red);       // [NW][BT]
-    float* redB = redA + NW * BT;                                    // [NW][BT]
-    float* redC = redB + NW * BT;                                    // [NW][5][BT]
+    float* redA = reinterpret_cast<float*>(smem + L::off_red);       // [MW][BT]
+    float* redB = redA + LS_MW * BT;                                 // [MW][BT]
+    float* redC = redB + LS_MW * BT;                                 // [MW][5][BT]
     int* flag = reinterpret_cast<int*>(smem + L::off_flag);
     uint64_t* bar_tile = reinterpret_cast<uint64_t*>(smem + L::off_bar);   // [LS_NSLOT]
     uint64_t* bar_w1 = bar_tile + LS_NSLOT;
@@ -377,20 +486,20 @@ ls_member_kernel(const __grid_constant__ CUtensorMap map_w2, const LsMemberParam
         mbar_fence_init();
     }
     __syncthreads();
-    // tile sequence s = i * 8 + w: the i-th tile of warp w = row quarter (w & 3), k-tile (w >> 2) * 16 + i;
-    // it lives in slot s % 16, so warp w double-buffers its own stream in slots w and w + 8.
+    // tile sequence s = i * 4 + w: the i-th tile of warp w = row half (w & 1), k-tile (w >> 1) * 16 + i;
+    // it lives in slot s % 8, so warp w double-buffers its own stream in slots w and w + 4.
     auto issue_tile = [&](int s) {
-        const int w = s & 7, i = s >> 3, slot = s & (LS_NSLOT - 1);
-        const int kt = (w >> 2) * LS_TPW + i, rq = w & 3;
+        const int w = s & 3, i = s >> 2, slot = s & (LS_NSLOT - 1);
+        const int kt = (w >> 1) * LS_TPW + i, rh = w & 1;
         mbar_arrive_expect_tx(bar_tile + slot, LS_TILE_BYTES);
-        tma_load_3d(ring + (size_t)slot * LS_TILE_BYTES, &map_w2, bar_tile + slot, kt * LS_TILE_K, rq * 64, m);
+        tma_load_3d(ring + (size_t)slot * LS_TILE_BYTES, &map_w2, bar_tile + slot, kt * LS_TILE_K, rh * LS_TILE_ROWS, m);
     };
     if (t == 0) {
         const uint32_t w1_bytes = (uint32_t)(H1 * in_dim + 3 * H1) * 4;
         mbar_arrive_expect_tx(bar_w1, w1_bytes);
         bulk_g2s(w1a, mrow, w1_bytes, bar_w1);
 #pragma unroll 1
-        for (int s = 0; s < LS_NSLOT / 2; ++s) issue_tile(s);      // every warp's first tile (slots 0..7)
+        for (int s = 0; s < LS_NSLOT / 2; ++s) issue_tile(s);      // every warp's first tile (slots 0..3)
         mbar_arrive_expect_tx(bar_tail, LS_TAIL_FLOATS * 4);
         bulk_g2s(tail, mrow + om.fc2b, LS_TAIL_FLOATS * 4, bar_tail);
     }
@@ -401,43 +510,49 @@ ls_member_kernel(const __grid_constant__ CUtensorMap map_w2, const LsMemberParam
     }
     __syncthreads();
     mbar_wait(bar_w1, 0);
-    if (p.seat == 0) layer1<BT, IN_ADV>(w1a, obs, h1p, red1, flag);
-    else layer1<BT, IN_GOOD>(w1a, obs, h1p, red1, flag);
-    __syncthreads();          // h1p complete; the W1 block is dead, slots 8..15 are free
+    if (p.seat == 0) ls_layer1<IN_ADV>(w1a, obs, h1p, red1, flag);
+    else ls_layer1<IN_GOOD>(w1a, obs, h1p, red1, flag);
+    __syncthreads();          // h1p complete; the W1 block is dead, slots 4..7 are free
     if (lane == 0) {
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic reads of W1 before the TMA writes
-        issue_tile(8 + warp);
+        issue_tile(4 + warp);
     }
 
-    // ---- fc2: warp w = (row quarter w & 3, k half w >> 2), 16 tiles of [64 x 16] ---------------
-    float2 acc[8][4];
+    // ---- fc2: warp w = (row half w & 1, k half w >> 1), 16 tiles of [128 x 16] -----------------
+    float2 acc[8][8];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
+        for (int j = 0; j < 8; ++j) acc[i][j] = make_float2(0.f, 0.f);
 #pragma unroll 1
     for (int i = 0; i < LS_TPW; ++i) {
-        const int slot = warp + 8 * (i & 1);
+        const int slot = warp + 4 * (i & 1);
         mbar_wait(bar_tile + slot, (uint32_t)(i >> 1));
         ls_fc2_tile(reinterpret_cast<const float4*>(ring + (size_t)slot * LS_TILE_BYTES), h1p,
-                    ((warp >> 2) * LS_TPW + i) * LS_TILE_K, acc);
+                    ((warp >> 1) * LS_TPW + i) * LS_TILE_K, acc);
         __syncwarp();
-        if (lane == 0 && i + 2 < LS_TPW) issue_tile((i + 2) * 8 + warp);
+        if (lane == 0 && i + 2 < LS_TPW) issue_tile((i + 2) * 4 + warp);
     }
     __syncthreads();          // every warp is done reading h1p
     {
         float* part = h1p;    // [2 k-halves][256 rows][BT]
-        const int eg = lane & 3, rl = lane >> 2;
-        const int kh = warp >> 2, rq = warp & 3;
+        const int eg = lane & 1, rl = lane >> 1;
+        const int kh = warp >> 1, rh = warp & 1;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int row = rq * 64 + rl + 8 * i;
-            float4 v;
-            v.x = acc[i][0].x + acc[i][0].y;
-            v.y = acc[i][1].x + acc[i][1].y;
-            v.z = acc[i][2].x + acc[i][2].y;
-            v.w = acc[i][3].x + acc[i][3].y;
-            *reinterpret_cast<float4*>(part + ((size_t)(kh * H2 + row)) * BT + eg * 4) = v;
+            const int row = rh * LS_TILE_ROWS + rl + 16 * i;
+            float* dst = part + ((size_t)(kh * H2 + row)) * BT + eg * 8;
+            float4 v0, v1;
+            v0.x = acc[i][0].x + acc[i][0].y;
+            v0.y = acc[i][1].x + acc[i][1].y;
+            v0.z = acc[i][2].x + acc[i][2].y;
+            v0.w = acc[i][3].x + acc[i][3].y;
+            v1.x = acc[i][4].x + acc[i][4].y;
+            v1.y = acc[i][5].x + acc[i][5].y;
+            v1.z = acc[i][6].x + acc[i][6].y;
+            v1.w = acc[i][7].x + acc[i][7].y;
+            *reinterpret_cast<float4*>(dst) = v0;
+            *reinterpret_cast<float4*>(dst + 4) = v1;
         }
     }
     __syncthreads();
@@ -461,7 +576,7 @@ ls_member_kernel(const __grid_constant__ CUtensorMap map_w2, const LsMemberParam
     __syncthreads();
     float mean = 0.f;
 #pragma unroll
-    for (int w = 0; w < NW; ++w) mean += redA[w * BT + e1];
+    for (int w = 0; w < LS_MW; ++w) mean += redA[w * BT + e1];
     mean *= (1.0f / H2);
     float lsq = 0.f;
 #pragma unroll
@@ -474,7 +589,7 @@ ls_member_kernel(const __grid_constant__ CUtensorMap map_w2, const LsMemberParam
     __syncthreads();
     float var = 0.f;
 #pragma unroll
-    for (int w = 0; w < NW; ++w) var += redB[w * BT + e1];
+    for (int w = 0; w < LS_MW; ++w) var += redB[w * BT + e1];
     var *= (1.0f / H2);
     if (!isfinite(mean) || !isfinite(var)) *flag = 1;
     const float rstd = 1.0f / sqrtf(var + LN_EPS);
@@ -499,7 +614,7 @@ ls_member_kernel(const __grid_constant__ CUtensorMap map_w2, const LsMemberParam
         for (int a = 0; a < NACT; ++a) {
             float v = redC[a * BT + t];
 #pragma unroll
-            for (int w = 1; w < NW; ++w) v += redC[(w * NACT + a) * BT + t];
+            for (int w = 1; w < LS_MW; ++w) v += redC[(w * NACT + a) * BT + t];
             lg[a] = v + b3[a];
             fin = fin && isfinite(lg[a]);
         }
@@ -966,7 +1081,7 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
         const FcOffsets om = fc_offsets(seat_in_dim(ms));
         cuuint64_t dims[3] = {(cuuint64_t)H1, (cuuint64_t)H2, (cuuint64_t)p.P};
         cuuint64_t strides[2] = {(cuuint64_t)H1 * 4, (cuuint64_t)p.member_pitch * 4};
-        cuuint32_t box[3] = {LS_TILE_K, 64, 1};
+        cuuint32_t box[3] = {LS_TILE_K, LS_TILE_ROWS, 1};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = encode(&map_w2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.members + om.fc2w), dims,
                             strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
@@ -1073,7 +1188,7 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
         }
         if (!(skip & 2)) {
             tick(0, 0);
-            ls_member_kernel<<<(unsigned)member_ctas, CT, LsMemberSmem::total, stream>>>(map_w2, mp);
+            ls_member_kernel<<<(unsigned)member_ctas, LS_MT, LsMemberSmem::total, stream>>>(map_w2, mp);
             tick(0, 1);
         }
         if (fork && !(skip & 1)) CEV_CUDA(cudaStreamWaitEvent(stream, h->join_ev, 0));
