@@ -63,6 +63,8 @@ _SIGNATURES = {
                                    c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "cev_es_update_f32": (c_int, [c_void_p, c_void_p, c_int, c_float, c_float, c_int64,
                                   c_uint64, c_int, c_uint32, c_int64, c_int64, c_void_p, c_void_p]),
+    "cev_es_update_members_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_float, c_float,
+                                          c_int64, c_int64, c_void_p, c_void_p]),
     "cev_axpy_f32": (c_int, [c_void_p, c_float, c_void_p, c_void_p, c_int64, c_void_p]),
     "cev_diversity_dist_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int,
                                        c_void_p, c_void_p]),

@@ -204,13 +204,19 @@ __device__ __forceinline__ float u01(uint32_t x) {
     return __fmaf_rn(__uint2float_rn(x), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
 }
 
+// Box-Muller with the sine / cosine on the SFU (MUFU.SIN / MUFU.COS, absolute error 2^-21.2 on [-pi, pi]):
+// the normals of K3/K5/K6 are ALU bound (141 M per ES role and generation) and sincospif was the largest
+// part of that cost.  The logarithm stays libm-accurate (near u1 = 1 the SFU log2 has no relative accuracy
+// left and r = sqrt(-2 log u1) would be off by up to 5e-4).  Absolute error of a normal vs the fp64-accurate
+// value: a few 1e-6; every consumer regenerates noise with this same function, so the streams agree.
 __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float& z0, float& z1) {
     const float u1 = u01(xa), u2 = u01(xb);
-    const float r = sqrtf(-2.0f * logf(u1));
+    const float r = sqrtf(-2.0f * logf(u1));     // libm-accurate: __logf loses all relative accuracy near u1 = 1
+    // MUFU.SIN / MUFU.COS are accurate on [-pi, pi]: evaluate at 2 pi u - pi and flip both signs
     float s, c;
-    sincospif(2.0f * u2, &s, &c);
-    z0 = r * c;
-    z1 = r * s;
+    __sincosf(6.283185307179586f * (u2 - 0.5f), &s, &c);
+    z0 = -(r * c);
+    z1 = -(r * s);
 }
 
 // four standard normals for flat parameter indices 4*j4 .. 4*j4+3 of `member`

@@ -106,6 +106,34 @@ __global__ void __launch_bounds__(PT) es_update_partial_kernel(
         make_float4(acc[0], acc[1], acc[2], acc[3]);
 }
 
+// The same partial sums from the MATERIALISED members: sigma z_i = member_i - theta up to one rounding
+// of the perturbation's add (1e-7 relative), read back at HBM speed instead of regenerating P normals per
+// parameter on the ALU.  LayerNorm entries are copies of theta, so they contribute exact zeros.
+__global__ void __launch_bounds__(PT) es_update_members_partial_kernel(
+    const double* __restrict__ fitness, const float* __restrict__ members, const float* __restrict__ theta,
+    int64_t pitch, int64_t n_rows, int n_split, float* __restrict__ partial) {
+    const int j4 = blockIdx.x * PT + threadIdx.x;
+    if ((int64_t)j4 * 4 >= pitch) return;
+    const int sp = blockIdx.y;
+    const int64_t per = (n_rows + n_split - 1) / n_split;
+    const int64_t r_lo = sp * per, r_hi = min(n_rows, r_lo + per);
+    const float4 t4 = *reinterpret_cast<const float4*>(theta + (int64_t)j4 * 4);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const float4* col = reinterpret_cast<const float4*>(members) + j4;
+    const int64_t stride4 = pitch / 4;
+#pragma unroll 8
+    for (int64_t r = r_lo; r < r_hi; ++r) {
+        const float f = (float)fitness[r];
+        const float4 m = __ldcs(col + r * stride4);
+        acc[0] = fmaf(__fsub_rn(m.x, t4.x), f, acc[0]);
+        acc[1] = fmaf(__fsub_rn(m.y, t4.y), f, acc[1]);
+        acc[2] = fmaf(__fsub_rn(m.z, t4.z), f, acc[2]);
+        acc[3] = fmaf(__fsub_rn(m.w, t4.w), f, acc[3]);
+    }
+    *reinterpret_cast<float4*>(partial + (int64_t)sp * pitch + (int64_t)j4 * 4) =
+        make_float4(acc[0], acc[1], acc[2], acc[3]);
+}
+
 __global__ void __launch_bounds__(PT) es_update_finish_kernel(
     const float* __restrict__ partial, int n_split, int64_t pitch, float coef,
     float* __restrict__ delta) {
@@ -421,6 +449,30 @@ int cev_es_update_f32(cev_handle* h, const double* fitness, int in_dim, float si
     es_update_finish_kernel<<<(unsigned)((pitch + PT - 1) / PT), PT, 0, (cudaStream_t)stream>>>(partial, n_split,
                                                                                               pitch, coef, delta);
     return check_cuda(cudaGetLastError(), "es_update kernels");
+}
+
+int cev_es_update_members_f32(cev_handle* h, const double* fitness, const float* members, int64_t pitch,
+                              const float* theta, int in_dim, float sigma, float lr, int64_t n_total,
+                              int64_t n_rows, float* delta, cev_stream stream) {
+    CEV_REQUIRE(h && fitness && members && theta && delta, "es_update_members: null pointer");
+    CEV_REQUIRE(in_dim == IN_ADV || in_dim == IN_GOOD, "es_update_members: in_dim must be 8 or 10");
+    CEV_REQUIRE(n_total >= 1 && n_rows >= 0 && sigma > 0.f, "es_update_members: bad n/sigma");
+    CEV_REQUIRE(pitch == fc_pitch(in_dim), "es_update_members: rows must use the padded pitch cev_fc_pitch(in_dim)");
+    CEV_REQUIRE(aligned16(delta) && aligned16(members) && aligned16(theta), "es_update_members: 16B alignment");
+    int n_split = (int)((n_rows + 31) / 32);
+    if (n_split > 32) n_split = 32;
+    if (n_split < 1) n_split = 1;
+    int rc = ensure_workspace(h, (size_t)n_split * pitch * sizeof(float));
+    if (rc) return rc;
+    float* partial = static_cast<float*>(h->workspace);
+    dim3 grid((unsigned)((pitch / 4 + PT - 1) / PT), (unsigned)n_split);
+    es_update_members_partial_kernel<<<grid, PT, 0, (cudaStream_t)stream>>>(fitness, members, theta, pitch, n_rows,
+                                                                           n_split, partial);
+    CEV_CUDA(cudaGetLastError());
+    const float coef = (float)((double)lr / ((double)n_total * (double)sigma));
+    es_update_finish_kernel<<<(unsigned)((pitch + PT - 1) / PT), PT, 0, (cudaStream_t)stream>>>(partial, n_split,
+                                                                                              pitch, coef, delta);
+    return check_cuda(cudaGetLastError(), "es_update_members kernels");
 }
 
 int cev_axpy_f32(cev_handle* h, float a, const float* x, float* y, int64_t n, cev_stream stream) {

@@ -115,7 +115,10 @@ class _EngineBase:
         self.overlap_roles = bool(getattr(args, "overlap_roles", True)) and self.device.type == "cuda"
         self._role_streams = None
         #: form each role's update on the role's stream right after its rollout (ES)
-        self.early_update = bool(getattr(args, "early_update", True))
+        self.early_update = bool(getattr(args, "early_update", False))
+        #: ES update from the materialised members (K6 as an HBM-bound read) instead of regenerating the
+        #: noise from the Philox key (K6 as ALU work); both are within fp32 rounding of each other
+        self.update_from_members = bool(getattr(args, "update_from_members", True))
 
     # initial states of `n_rows` x K x E episodes for the rows [row0, row0+n_local) of a
     # P-row evaluation; in reference mode every rank draws the whole block to keep the
@@ -385,7 +388,11 @@ class ESEngine(_EngineBase):
                 fit_local = (fit_local.to(torch.float32) / (1 + div)).to(torch.float64)
             self.fitness[role] = self.comm.all_gather_rows(fit_local.contiguous(), self.shard)
             delta, self._delta_local[role] = self._delta_local.get(role), None
-            if delta is None:
+            if delta is None and self.update_from_members and hasattr(self.k, "es_update_members"):
+                # sigma*z_i read back from the materialised members (HBM bound) instead of regenerated
+                delta = self.k.es_update_members(fit_local.contiguous(), self.members[role], self.theta[role],
+                                                 in_dim, self.sigma(role), a.learning_rate, self.P)
+            elif delta is None:
                 delta = self.k.es_update(fit_local.contiguous(), in_dim, self.sigma(role), a.learning_rate, self.P,
                                          self.seed, role, self.gen, self.shard.row0)
             self.comm.all_reduce_sum(delta)

@@ -16,7 +16,7 @@ from ._lib import RolloutCfg, check, handle, load
 MAX_CYCLES = 25
 
 #: kernels launched per C-ABI call (bench.py reports the total as ``gpu_launches``)
-_KERNELS_PER_CALL = {"cev_es_update_f32": 2, "cev_fp32_peak": 4}
+_KERNELS_PER_CALL = {"cev_es_update_f32": 2, "cev_es_update_members_f32": 2, "cev_fp32_peak": 4}
 launch_count = 0
 
 
@@ -253,6 +253,23 @@ def es_update(fitness, in_dim, sigma, lr, n_total, seed, role, gen, row0, *, out
         _h(dev), _ptr(fitness), int(in_dim), float(sigma), float(lr), int(n_total),
         int(seed), role_id, int(gen), int(row0), fitness.shape[0], _ptr(out), _stream(dev)),
         "cev_es_update_f32")
+    return out
+
+
+def es_update_members(fitness, members, theta, in_dim, sigma, lr, n_total, *, out=None):
+    """K6 from the materialised members: delta fp32[pitch] = lr/(n_total*sigma) * sum_i (members[i] - theta)
+    * fitness_i (the reference's `noises` array read back instead of regenerated)."""
+    dev = _need_cuda(fitness, members, theta, out)
+    if fitness.dtype != torch.float64 or fitness.shape[0] != members.shape[0]:
+        raise _lib.CevError("es_update_members: fitness must be float64 [n_rows]")
+    pitch = layout.fc_pitch(in_dim)
+    if members.stride(0) != pitch or theta.numel() < pitch:
+        raise _lib.CevError("es_update_members: members / theta must use the padded row pitch")
+    if out is None:
+        out = torch.empty(pitch, dtype=torch.float32, device=dev)
+    check(_call("cev_es_update_members_f32", _h(dev), _ptr(fitness), _ptr(members), pitch, _ptr(theta),
+                int(in_dim), float(sigma), float(lr), int(n_total), members.shape[0], _ptr(out), _stream(dev)),
+          "cev_es_update_members_f32")
     return out
 
 

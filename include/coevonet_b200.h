@@ -191,6 +191,16 @@ int cev_es_update_f32(cev_handle* h, const double* fitness, int in_dim,
                       int64_t row0, int64_t n_rows,
                       float* delta, cev_stream stream);
 
+/*
+ * K6, from the materialised members: the same delta with sigma*z_i taken as members[i] - theta (the
+ * rows cev_es_perturb_f32 wrote, pitch = cev_fc_pitch(in_dim)), i.e. the `noises` array of
+ * compute_weight_update read back at HBM speed instead of regenerated on the ALU.  Differs from
+ * cev_es_update_f32 by one rounding of the perturbation's add per term (1e-7 relative).
+ */
+int cev_es_update_members_f32(cev_handle* h, const double* fitness, const float* members, int64_t pitch,
+                              const float* theta, int in_dim, float sigma, float lr, int64_t n_total,
+                              int64_t n_rows, float* delta, cev_stream stream);
+
 /* theta[j] += delta[j] (evolutionary_strategy.py:259-265) */
 int cev_axpy_f32(cev_handle* h, float a, const float* x, float* y, int64_t n, cev_stream stream);
 

@@ -171,3 +171,22 @@ def test_fp32_peak_probe_runs():
     t1 = ops.fp32_peak("cuda:0", 1)
     assert 5 < t0 < 200 and 5 < t1 < 200
     print(f"fp32 peak: scalar FFMA {t0:.1f} TFLOP/s, FFMA2 {t1:.1f} TFLOP/s")
+
+
+def test_es_update_from_members_matches_regenerated_update():
+    """K6 read back from the materialised members (members - theta = sigma*z up to one rounding) vs K6
+    regenerated from the Philox key: same delta to 1e-6 of its scale, exact zeros on LayerNorm rows."""
+    from coevonet_b200 import layout, ops
+    from oracle import weights
+    P, in_dim, sigma, lr, seed = 300, 10, 0.05, 0.1, 77
+    pitch = layout.fc_pitch(in_dim)
+    theta = torch.zeros(pitch, device="cuda")
+    theta[:layout.fc_dim(in_dim)] = torch.from_numpy(weights.make_fc_rows(1, in_dim, 5)[0]).cuda()
+    members = ops.es_perturb(theta, in_dim, sigma, seed, "agent_1", 3, 0, P)
+    fit = torch.randn(P, dtype=torch.float64, device="cuda")
+    want = ops.es_update(fit, in_dim, sigma, lr, P, seed, "agent_1", 3, 0)
+    got = ops.es_update_members(fit, members, theta, in_dim, sigma, lr, P)
+    scale = float(want.abs().max())
+    assert scale > 0
+    assert float((got - want).abs().max()) <= 1e-6 * scale + 1e-9
+    assert torch.equal(got == 0, want == 0)            # LayerNorm entries and padding stay exactly zero
