@@ -723,8 +723,71 @@ __device__ __forceinline__ void op_produce_chunk(const float* __restrict__ w1a, 
     }
 }
 
-__global__ void __launch_bounds__(OP_THREADS, 1)
-ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
+// ---- CTA-pair (cta_group::2) plumbing ---------------------------------------------------------
+// In the PAIR form two CTAs on neighbouring SMs share one job of 256 episode rows: each produces the A
+// tile of its own 128 rows and holds HALF of the opponent matrix tile (128 of the 256 fc2 rows); one
+// tcgen05.mma.cta_group::2 (M = 256) issued by the leader drives both tensor cores, which exchange the B
+// halves over the pair link.  Per SM that is 8 KB of operand fetch per MMA instead of 12 KB and half the
+// TMA stream.  (Measured: no faster here, see launch_rollout_lockstep; kept as an opt-in.)  Barriers live at the same offsets
+// in both CTAs; "full" and "accumulator drained" are collected on the leader (remote arrives, TMA
+// complete_tx routed with the peer bit cleared), "empty" and "accumulator ready" are multicast commits.
+constexpr uint32_t CEV_PEER_MASK = 0xFEFFFFFFu;       // shared::cluster address of the same offset in the even CTA
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// arrive on the barrier at this offset in the LEADER CTA (a plain local arrive when executed by the leader)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(tc_smem_u32(bar) & CEV_PEER_MASK)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::
+            "r"(tc_smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(tc_smem_u32(bar) & CEV_PEER_MASK), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(
+                     tc_smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+constexpr uint32_t OP_IDESC_PAIR = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(256 >> 3) << 17) |
+                                   ((uint32_t)(256 >> 4) << 24);
+__device__ __forceinline__ void op_umma_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(OP_IDESC_PAIR), "r"(accumulate)
+        : "memory");
+}
+
+// stage geometry of the two forms
+template <bool PAIR>
+struct OpGeo {
+    static constexpr uint32_t B_BYTES = PAIR ? OP_B_BYTES / 2 : OP_B_BYTES;          // B hi (or lo) tile held by one CTA
+    static constexpr uint32_t STAGE_BYTES = 2 * OP_A_BYTES + 2 * B_BYTES;            // 96 KB / 64 KB
+    static constexpr int STAGES = PAIR ? 3 : 2;
+    static_assert((size_t)STAGES * STAGE_BYTES == OP_OFF_W1A, "both forms use the same 192 KB of stages");
+    static constexpr int ROWS_PER_JOB = PAIR ? 2 * OP_BM : OP_BM;
+    static constexpr uint32_t N_FULL = (PAIR ? 2 : 1) * (OP_PROD / 32) + 1;          // producer warps (of both CTAs) + TMA
+    static constexpr uint32_t N_TEMPTY = PAIR ? 8 : 4;
+};
+
+template <bool PAIR>
+__device__ __forceinline__ void ls_opp_body(const CUtensorMap& map_b, const LsOppParams& p) {
+    using Geo = OpGeo<PAIR>;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const int job0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int job_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     extern __shared__ unsigned char op_raw[];
     const uint32_t pad = (1024u - (smem_u32(op_raw) & 1023u)) & 1023u;
     if (pad > OP_SLACK) __trap();          // dynamic shared memory starts 1 KB aligned on sm_100; checked, not assumed
@@ -733,8 +796,8 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
     float* w1a = reinterpret_cast<float*>(base + OP_OFF_W1A);
     float* tail = reinterpret_cast<float*>(base + OP_OFF_TAIL);
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(base + OP_OFF_BAR);   // [2] A written + B landed
-    uint64_t* bar_empty = bar_full + OP_STAGES;                             // [2] MMAs retired
-    uint64_t* bar_tfull = bar_empty + OP_STAGES;                            // [2] accumulator ready
+    uint64_t* bar_empty = bar_full + Geo::STAGES;                           // [STAGES] MMAs retired
+    uint64_t* bar_tfull = bar_empty + Geo::STAGES;                          // [2] accumulator ready
     uint64_t* bar_tempty = bar_tfull + 2;                                   // [2] accumulator drained
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
     int* flag = reinterpret_cast<int*>(tmem_slot + 1);
@@ -743,24 +806,35 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
 
     if (threadIdx.x == 0) {
         *flag = 0;
-        for (int i = 0; i < OP_STAGES; ++i) {
-            tc_mbar_init(bar_full + i, OP_PROD + 1);
+        for (int i = 0; i < Geo::STAGES; ++i) {
+            tc_mbar_init(bar_full + i, Geo::N_FULL);
             tc_mbar_init(bar_empty + i, 1);
         }
         for (int i = 0; i < 2; ++i) {
             tc_mbar_init(bar_tfull + i, 1);
-            tc_mbar_init(bar_tempty + i, 4);
+            tc_mbar_init(bar_tempty + i, Geo::N_TEMPTY);
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
+    if (PAIR) cluster_sync_all();          // both CTAs' barriers exist before anything can reach them
     if (warp == 13) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tc_smem_u32(tmem_slot)),
-                     "r"(512u)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                             tc_smem_u32(tmem_slot)),
+                         "r"(512u)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                             tc_smem_u32(tmem_slot)),
+                         "r"(512u)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
+    if (PAIR) cluster_sync_all();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     const int jobs_per_ok = p.n_tiles;
@@ -775,7 +849,7 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
         const float* be2 = tail + 2 * H2;
         const float* w3 = tail + 3 * H2;
         const float* b3 = tail + 3 * H2 + NACT * H2;
-        for (int job = blockIdx.x; job < p.n_jobs; job += gridDim.x, ++pass) {
+        for (int job = job0; job < p.n_jobs; job += job_stride, ++pass) {
             const int okey = job / jobs_per_ok, tile = job % jobs_per_ok;
             const int oi = okey / p.K, k = okey % p.K;
             const int seat = oi ? p.seat[1] : p.seat[0];
@@ -789,7 +863,7 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
                 asm volatile("bar.sync 2, 128;\n" ::: "memory");
                 cur_ok = okey;
             }
-            const int64_t j = (int64_t)tile * OP_BM + q * 32 + lane;
+            const int64_t j = (int64_t)tile * Geo::ROWS_PER_JOB + rank * OP_BM + q * 32 + lane;
             const bool valid = j < p.PE;
             const int64_t jj = valid ? j : p.PE - 1;
             const int64_t ep = ((jj / p.E) * p.K + k) * p.E + (jj % p.E);
@@ -861,7 +935,10 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
             }
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             __syncwarp();
-            if (lane == 0) tc_mbar_arrive(bar_tempty + as);
+            if (lane == 0) {
+                if (PAIR) mbar_arrive_leader(bar_tempty + as);
+                else tc_mbar_arrive(bar_tempty + as);
+            }
             bool fin = isfinite(mean) && isfinite(var);
 #pragma unroll
             for (int a = 0; a < NACT; ++a) {
@@ -882,7 +959,7 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
         const int c = pt >> 5;                        // producer warp = 16-byte chunk (4 k) of every k-tile
         int cur_ok = -1;
         uint32_t it = 0;
-        for (int job = blockIdx.x; job < p.n_jobs; job += gridDim.x) {
+        for (int job = job0; job < p.n_jobs; job += job_stride) {
             const int okey = job / jobs_per_ok, tile = job % jobs_per_ok;
             const int oi = okey / p.K, k = okey % p.K;
             const int seat = oi ? p.seat[1] : p.seat[0];
@@ -900,7 +977,7 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
             float x[4][IN_GOOD];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int64_t jrow = (int64_t)tile * OP_BM + lane + 32 * j;
+                const int64_t jrow = (int64_t)tile * Geo::ROWS_PER_JOB + rank * OP_BM + lane + 32 * j;
                 const int64_t jj = jrow < p.PE ? jrow : p.PE - 1;
                 const int64_t ep = ((jj / p.E) * p.K + k) * p.E + (jj % p.E);
                 const float4* src = reinterpret_cast<const float4*>(p.obs + ((int64_t)seat * p.N + ep) * LS_OBS_PAD);
@@ -912,10 +989,10 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
             // the job's first stage: acquire it now, its A-hi tile doubles as the exchange buffer of the
             // LayerNorm-1 statistics (computed once per row by warps 0..3, read by all eight)
             {
-                const uint32_t st = it % OP_STAGES, use = it / OP_STAGES;
+                const uint32_t st = it % Geo::STAGES, use = it / Geo::STAGES;
                 if (use > 0) tc_mbar_wait(bar_empty + st, (use - 1) & 1);
             }
-            float2* xch = reinterpret_cast<float2*>(stage_mem + (size_t)(it % OP_STAGES) * OP_STAGE_BYTES);
+            float2* xch = reinterpret_cast<float2*>(stage_mem + (size_t)(it % Geo::STAGES) * Geo::STAGE_BYTES);
             if (c < 4) {
                 // closed form (fp64): mean = wbar . z, var = z^T C z, z = [x; 1], for row lane + 32 c
                 const double* S = p.l1stats + (size_t)okey * LS_L1S;
@@ -951,9 +1028,9 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
             }
             asm volatile("bar.sync 1, 256;\n" ::: "memory");          // exchange buffer read: the tile may be written
             for (int kt = 0; kt < OP_KT; ++kt, ++it) {
-                const uint32_t st = it % OP_STAGES, use = it / OP_STAGES;
+                const uint32_t st = it % Geo::STAGES, use = it / Geo::STAGES;
                 if (kt > 0 && use > 0) tc_mbar_wait(bar_empty + st, (use - 1) & 1);
-                unsigned char* a_hi = stage_mem + (size_t)st * OP_STAGE_BYTES;
+                unsigned char* a_hi = stage_mem + (size_t)st * Geo::STAGE_BYTES;
                 unsigned char* a_lo = a_hi + OP_A_BYTES;
 #if !(defined(CEV_EXP) && (CEV_EXP & 1))      // development experiment: bit 0 = producers write nothing
                 if (in == IN_GOOD) {
@@ -963,57 +1040,81 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
                 }
 #endif
                 asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic writes -> tensor core reads
-                tc_mbar_arrive(bar_full + st);
+                __syncwarp();
+                if (lane == 0) {                    // one arrival per producer warp
+                    if (PAIR) mbar_arrive_leader(bar_full + st);
+                    else tc_mbar_arrive(bar_full + st);
+                }
             }
         }
     } else if (warp == 12) {
         // ===================== TMA: pre-split opponent fc2 (hi | lo), [256 x 32] boxes ==========
         if (lane == 0) {
             uint32_t it = 0;
-            for (int job = blockIdx.x; job < p.n_jobs; job += gridDim.x) {
+            for (int job = job0; job < p.n_jobs; job += job_stride) {
                 const int okey = job / jobs_per_ok;
                 for (int kt = 0; kt < OP_KT; ++kt, ++it) {
-                    const uint32_t st = it % OP_STAGES, use = it / OP_STAGES;
+                    const uint32_t st = it % Geo::STAGES, use = it / Geo::STAGES;
                     if (use > 0) tc_mbar_wait(bar_empty + st, (use - 1) & 1);
-                    unsigned char* b_hi = stage_mem + (size_t)st * OP_STAGE_BYTES + 2 * OP_A_BYTES;
+                    unsigned char* b_hi = stage_mem + (size_t)st * Geo::STAGE_BYTES + 2 * OP_A_BYTES;
 #if defined(CEV_EXP) && (CEV_EXP & 2)         // development experiment: bit 1 = no opponent matrix stream
-                    tc_mbar_arrive(bar_full + st);
+                    if (!PAIR || rank == 0) tc_mbar_arrive(bar_full + st);
                     (void)b_hi;
 #else
-                    tc_mbar_expect_tx(bar_full + st, 2 * OP_B_BYTES);
-                    tma_load_2d(b_hi, &map_b, bar_full + st, kt * OP_BK, (okey * 2 + 0) * H2);
-                    tma_load_2d(b_hi + OP_B_BYTES, &map_b, bar_full + st, kt * OP_BK, (okey * 2 + 1) * H2);
+                    if (PAIR) {
+                        // both CTAs load their half of B hi / B lo; the bytes complete on the LEADER's barrier,
+                        // which expects all four boxes
+                        if (rank == 0) tc_mbar_expect_tx(bar_full + st, 4 * Geo::B_BYTES);
+                        tma_load_2d_pair(b_hi, &map_b, bar_full + st, kt * OP_BK, (okey * 2 + 0) * H2 + (int)rank * (H2 / 2));
+                        tma_load_2d_pair(b_hi + Geo::B_BYTES, &map_b, bar_full + st, kt * OP_BK,
+                                         (okey * 2 + 1) * H2 + (int)rank * (H2 / 2));
+                    } else {
+                        tc_mbar_expect_tx(bar_full + st, 2 * OP_B_BYTES);
+                        tma_load_2d(b_hi, &map_b, bar_full + st, kt * OP_BK, (okey * 2 + 0) * H2);
+                        tma_load_2d(b_hi + OP_B_BYTES, &map_b, bar_full + st, kt * OP_BK, (okey * 2 + 1) * H2);
+                    }
 #endif
                 }
             }
         }
-    } else {
-        // ===================== MMA issuer =====================
+    } else if (!PAIR || rank == 0) {
+        // ===================== MMA issuer (the leader CTA of a pair) =====================
         uint32_t it = 0, pass = 0;
-        for (int job = blockIdx.x; job < p.n_jobs; job += gridDim.x, ++pass) {
+        for (int job = job0; job < p.n_jobs; job += job_stride, ++pass) {
             const uint32_t as = pass & 1, ause = pass >> 1;
             if (ause > 0) tc_mbar_wait(bar_tempty + as, (ause - 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             const uint32_t d_tmem = tmem_base + as * OP_BN;
             for (int kt = 0; kt < OP_KT; ++kt, ++it) {
-                const uint32_t st = it % OP_STAGES, use = it / OP_STAGES;
+                const uint32_t st = it % Geo::STAGES, use = it / Geo::STAGES;
                 tc_mbar_wait(bar_full + st, use & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 if (lane == 0) {
-                    const uint32_t s_addr = tc_smem_u32(stage_mem + (size_t)st * OP_STAGE_BYTES);
+                    const uint32_t s_addr = tc_smem_u32(stage_mem + (size_t)st * Geo::STAGE_BYTES);
                     const uint64_t a_hi = umma_desc_sw128(s_addr);
                     const uint64_t a_lo = umma_desc_sw128(s_addr + OP_A_BYTES);
                     const uint64_t b_hi = umma_desc_sw128(s_addr + 2 * OP_A_BYTES);
-                    const uint64_t b_lo = umma_desc_sw128(s_addr + 2 * OP_A_BYTES + OP_B_BYTES);
+                    const uint64_t b_lo = umma_desc_sw128(s_addr + 2 * OP_A_BYTES + Geo::B_BYTES);
 #pragma unroll
                     for (int k8 = 0; k8 < OP_BK / 8; ++k8) {
                         const uint64_t ko = (uint64_t)(k8 * 2);           // 8 tf32 = 32 bytes
-                        op_umma(d_tmem, a_lo + ko, b_hi + ko, (kt | k8) ? 1u : 0u);   // small terms first
-                        op_umma(d_tmem, a_hi + ko, b_lo + ko, 1u);
-                        op_umma(d_tmem, a_hi + ko, b_hi + ko, 1u);
+                        if (PAIR) {
+                            op_umma_pair(d_tmem, a_lo + ko, b_hi + ko, (kt | k8) ? 1u : 0u);   // small terms first
+                            op_umma_pair(d_tmem, a_hi + ko, b_lo + ko, 1u);
+                            op_umma_pair(d_tmem, a_hi + ko, b_hi + ko, 1u);
+                        } else {
+                            op_umma(d_tmem, a_lo + ko, b_hi + ko, (kt | k8) ? 1u : 0u);
+                            op_umma(d_tmem, a_hi + ko, b_lo + ko, 1u);
+                            op_umma(d_tmem, a_hi + ko, b_hi + ko, 1u);
+                        }
                     }
-                    umma_commit(bar_empty + st);
-                    if (kt == OP_KT - 1) umma_commit(bar_tfull + as);
+                    if (PAIR) {
+                        umma_commit_pair(bar_empty + st);
+                        if (kt == OP_KT - 1) umma_commit_pair(bar_tfull + as);
+                    } else {
+                        umma_commit(bar_empty + st);
+                        if (kt == OP_KT - 1) umma_commit(bar_tfull + as);
+                    }
                 }
                 __syncwarp();
             }
@@ -1021,11 +1122,28 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
+    if (PAIR) cluster_sync_all();          // the peer's tensor core may still read this CTA's shared memory / TMEM
     if (threadIdx.x == 0 && *flag && p.status) atomicOr(p.status, CEV_STATUS_NONFINITE);
     if (warp == 13) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u) : "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u) : "memory");
+        } else {
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u) : "memory");
+        }
     }
 }
+
+__global__ void __launch_bounds__(OP_THREADS, 1)
+ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
+    ls_opp_body<false>(map_b, p);
+}
+
+// CTA-pair form: clusters of two CTAs, tcgen05 cta_group::2 (M = 256 per MMA)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(OP_THREADS, 1)
+ls_opp_pair_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
+    ls_opp_body<true>(map_b, p);
+}
+
 
 // ---------------------------------------------------------------------------------------------
 // host side
@@ -1059,6 +1177,7 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
                                       (int)LsMemberSmem::total));
         CEV_CUDA(cudaFuncSetAttribute(ls_member_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CEV_CUDA(cudaFuncSetAttribute(ls_opp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OP_SMEM));
+        CEV_CUDA(cudaFuncSetAttribute(ls_opp_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OP_SMEM));
         configured[h->device] = true;
     }
 
@@ -1140,7 +1259,13 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
     op.K = p.K;
     op.E = p.E;
     op.PE = (int64_t)p.P * p.E;
-    op.n_tiles = (int)((op.PE + OP_BM - 1) / OP_BM);
+    // CEV_LS_PAIR=1 selects the CTA-pair (cta_group::2) form of the opponent kernel.  It is parity-green but
+    // 8-10 % slower than the single-CTA form on this workload: the MMA chain alone already runs at the
+    // MEASURED dense TF32 rate (half of MEASURED_PEAKS.json's bf16 figure) in both forms, so sharing the B
+    // operand buys nothing and the cross-CTA barrier traffic costs a little.
+    static const int use_pair = getenv("CEV_LS_PAIR") ? atoi(getenv("CEV_LS_PAIR")) : 0;
+    const int rows_per_job = use_pair ? 2 * OP_BM : OP_BM;
+    op.n_tiles = (int)((op.PE + rows_per_job - 1) / rows_per_job);
     op.n_jobs = 2 * p.K * op.n_tiles;
     op.N = N;
     op.obs = b.obs;
@@ -1148,7 +1273,23 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
     op.gap = b.gap;
     op.l1stats = b.l1stats;
     op.status = p.status;
-    const int opp_grid = op.n_jobs < h->n_sm ? op.n_jobs : h->n_sm;
+    int opp_grid = op.n_jobs < h->n_sm ? op.n_jobs : h->n_sm;
+    if (use_pair) {
+        const int pairs = h->n_sm / 2;
+        opp_grid = 2 * (op.n_jobs < pairs ? op.n_jobs : pairs);
+        // the pair form loads [128 x 32] boxes: one half of B per CTA
+        cuuint64_t dims[2] = {(cuuint64_t)H1, (cuuint64_t)2 * p.K * 2 * H2};
+        cuuint64_t strides[1] = {(cuuint64_t)H1 * 4};
+        cuuint32_t box[2] = {OP_BK, OP_BN / 2};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, b.w2split, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("rollout_lockstep: cuTensorMapEncodeTiled(opponent fc2, pair form) failed with %d", (int)r);
+            return CEV_ERR_CUDA;
+        }
+    }
 
     // development aids: CEV_LS_SKIP bit 0 = no opponent kernel, bit 1 = no member kernel (timing only,
     // results are then invalid); CEV_LS_FORK=1 = opponent kernel on a side stream beside the member kernel
@@ -1178,11 +1319,13 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
             if (fork) {
                 CEV_CUDA(cudaEventRecord(h->fork_ev, stream));
                 CEV_CUDA(cudaStreamWaitEvent(h->side_stream, h->fork_ev, 0));
-                ls_opp_kernel<<<opp_grid, OP_THREADS, OP_SMEM, h->side_stream>>>(map_b, op);
+                if (use_pair) ls_opp_pair_kernel<<<opp_grid, OP_THREADS, OP_SMEM, h->side_stream>>>(map_b, op);
+                else ls_opp_kernel<<<opp_grid, OP_THREADS, OP_SMEM, h->side_stream>>>(map_b, op);
                 CEV_CUDA(cudaEventRecord(h->join_ev, h->side_stream));
             } else {
                 tick(1, 0);
-                ls_opp_kernel<<<opp_grid, OP_THREADS, OP_SMEM, stream>>>(map_b, op);
+                if (use_pair) ls_opp_pair_kernel<<<opp_grid, OP_THREADS, OP_SMEM, stream>>>(map_b, op);
+                else ls_opp_kernel<<<opp_grid, OP_THREADS, OP_SMEM, stream>>>(map_b, op);
                 tick(1, 1);
             }
         }

@@ -238,3 +238,19 @@ def test_large_population_stress_is_deterministic():
     idx = np.array([[k, i, k] for i in range(len(sel)) for k in range(K)])
     ref = orollout.rollout(nets, idx, init[sel].cpu().numpy().reshape(-1, 11))
     _compare(out1[sel].cpu().numpy().reshape(-1, 4), ref, "large-population sample")
+
+
+def test_lockstep_cta_pair_form_matches_oracle():
+    """The opt-in CTA-pair form of the opponent kernel (tcgen05 cta_group::2, M = 256 per MMA, B halves
+    exchanged over the pair link; CEV_LS_PAIR=1 is read once per process, so it runs in a child)."""
+    import os, subprocess, sys
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import test_gpu_rollout as t\n"
+        "out, ref = t._structured_case('agent_1', 70, 2, 9, seed=99, variant=3)\n"
+        "print(t._compare(out, ref, 'pair form'))\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CEV_LS_PAIR="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
