@@ -102,12 +102,14 @@ int cev_dqn_dim(int c_in, int n_actions) {
 }
 int cev_dqn_pitch(int c_in, int n_actions) { return round_up(cev_dqn_dim(c_in, n_actions), 32); }
 
-// Which K1 kernel a structured rollout uses: 1 generic, 2 cluster (member weights resident, best when a
-// member plays few episodes: GA), 3 lockstep (opponent forwards on tcgen05, best when every member
-// plays many episodes against shared opponents: ES).
+// Which K1 kernel a structured rollout uses: 1 generic, 2 cluster (member weights resident in shared
+// memory; small launches: evaluation games, tiny populations), 3 lockstep (opponent forwards on tcgen05,
+// member rows streamed once per world step).  Lockstep wins whenever there are enough episodes to fill
+// the opponent GEMM: 3.5x at the ES shape (16 episodes per member) and still 3.3x at the GA shape (one
+// episode per member), where its member kernel is purely HBM bound (5.8 TB/s).
 static int rollout_plan(const cev_handle* h, int P, int K, int E, int variant) {
     if (variant != 0) return variant;
-    if ((int64_t)P * K * E >= 2048 && K * E >= 8) return 3;
+    if ((int64_t)P * K * E >= 2048) return 3;
     return h->n_clusters > 0 ? 2 : 1;
 }
 

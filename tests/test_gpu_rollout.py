@@ -128,6 +128,7 @@ def test_lockstep_is_the_auto_choice_for_es_shapes_and_counts_its_launches():
     from coevonet_b200 import ops
     assert ops.rollout_plan(0, 1024, 1, 16) == (3, 3 + 3 * 25)
     assert ops.rollout_plan(0, 20, 3, 1)[0] == 2
+    assert ops.rollout_plan(0, 8192, 1, 1)[0] == 3          # GA shape at scale: lockstep too
     assert ops.rollout_plan(0, 1, 1, 10)[0] == 2
     assert ops.rollout_plan(0, 1024, 1, 16, variant=2) == (2, 3)
 
