@@ -18,39 +18,12 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "common.cuh"
+#include "deepqn_common.cuh"
 
 namespace cev {
 
 constexpr int DQ_T = 256;
 constexpr int DQ_FB = 12;                 // frames per fc pass (12 x (3136 + 512) floats = 175 KB of shared memory)
-constexpr float BN_EPS = 1e-5f;
-
-struct DqnOffsets {
-    int c1w, c1b, c2w, c2b, c3w, c3b, f1w, f1b, ow, ob, bn1g, bn1b, bn2g, bn2b, bn3g, bn3b, total;
-};
-
-__host__ __device__ inline DqnOffsets dqn_offsets(int c_in, int n_act) {
-    DqnOffsets o;
-    o.c1w = 0;
-    o.c1b = o.c1w + 32 * c_in * 64;
-    o.c2w = o.c1b + 32;
-    o.c2b = o.c2w + 64 * 32 * 16;
-    o.c3w = o.c2b + 64;
-    o.c3b = o.c3w + 64 * 64 * 9;
-    o.f1w = o.c3b + 64;
-    o.f1b = o.f1w + 512 * 3136;
-    o.ow = o.f1b + 512;
-    o.ob = o.ow + n_act * 512;
-    o.bn1g = o.ob + n_act;
-    o.bn1b = o.bn1g + 32;
-    o.bn2g = o.bn1b + 32;
-    o.bn2b = o.bn2g + 64;
-    o.bn3g = o.bn2b + 64;
-    o.bn3b = o.bn3g + 64;
-    o.total = o.bn3b + 64;
-    return o;
-}
 
 // stage conv weights W[cout][k] (global, k contiguous) as Wt[k][cout] in shared memory.
 // (A padded-tile transposition that removes the shared-memory store conflicts was measured
@@ -323,7 +296,7 @@ extern "C" int cev_deepqn_forward(cev_handle* h, const float* members, int P, in
     if (P == 0) return CEV_OK;
     // activation scratch (stays in L2 between the layer phases of a member)
     const size_t per = (size_t)P * B;
-    const size_t need = per * (12800 + 5184 + 3136) * sizeof(float);
+    const size_t need = per * (12800 + 5184 + 3136 + 3136) * sizeof(float);
     if (h->workspace_bytes < need) {
         if (h->workspace) CEV_CUDA(cudaFree(h->workspace));
         h->workspace = nullptr;
@@ -342,22 +315,35 @@ extern "C" int cev_deepqn_forward(cev_handle* h, const float* members, int P, in
     p.act1 = static_cast<float*>(h->workspace);
     p.act2 = p.act1 + per * 12800;
     p.act3 = p.act2 + per * 5184;
+    float* y3 = p.act3 + per * 3136;          // conv3's pre-BatchNorm output (tensor-core conv path)
     p.logits = logits;
     p.actions = actions;
-    // fully-connected stage: tcgen05 (TF32, default) or the fp32 CUDA-core loop (COEVONET_DQN_FC=fp32)
+    // fully-connected stage: tcgen05 (TF32, default) or the fp32 CUDA-core loop (COEVONET_DQN_FC=fp32);
+    // convolution stack: tcgen05 implicit GEMM (3xTF32, default with the tensor-core fc stage) or the fp32
+    // CUDA-core kernel (COEVONET_DQN_CONV=fp32, and always with COEVONET_DQN_FC=fp32: the tight-parity path)
     const char* fc_env = getenv("COEVONET_DQN_FC");
     const bool use_tc = !(fc_env && strcmp(fc_env, "fp32") == 0);
+    const char* conv_env = getenv("COEVONET_DQN_CONV");
+    const bool conv_tc = use_tc && !(conv_env && strcmp(conv_env, "fp32") == 0);
     p.skip_fc = use_tc ? 1 : 0;
-    const size_t smem = dqn_smem_bytes(c_in);
-    const int grid = P < h->n_sm ? P : h->n_sm;
-    if (c_in == 4) {
-        CEV_CUDA(cudaFuncSetAttribute(deepqn_forward_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        deepqn_forward_kernel<4><<<grid, DQ_T, smem, (cudaStream_t)stream>>>(p);
+    if (conv_tc) {
+        int rc = launch_deepqn_conv_tc(h, members, pitch, P, B, c_in, n_actions, frames, p.act1, p.act2, y3, p.act3,
+                                       (cudaStream_t)stream);
+        if (rc) return rc;
     } else {
-        CEV_CUDA(cudaFuncSetAttribute(deepqn_forward_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        deepqn_forward_kernel<6><<<grid, DQ_T, smem, (cudaStream_t)stream>>>(p);
+        const size_t smem = dqn_smem_bytes(c_in);
+        const int grid = P < h->n_sm ? P : h->n_sm;
+        if (c_in == 4) {
+            CEV_CUDA(cudaFuncSetAttribute(deepqn_forward_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem));
+            deepqn_forward_kernel<4><<<grid, DQ_T, smem, (cudaStream_t)stream>>>(p);
+        } else {
+            CEV_CUDA(cudaFuncSetAttribute(deepqn_forward_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem));
+            deepqn_forward_kernel<6><<<grid, DQ_T, smem, (cudaStream_t)stream>>>(p);
+        }
+        CEV_CUDA(cudaGetLastError());
     }
-    CEV_CUDA(cudaGetLastError());
     if (use_tc)
         return launch_deepqn_fc_tc(h, members, pitch, P, B, n_actions, o.f1w, o.f1b, o.ow, o.ob, p.act3, logits,
                                    actions, (cudaStream_t)stream);
