@@ -184,7 +184,14 @@ deepqn_conv_tc_kernel(const __grid_constant__ CUtensorMap map_w, const ConvParam
             } else {
                 // previous layer's output [positions][channels] -> channel-major rows, BatchNorm + ReLU applied
                 constexpr int NPIN = G::HIN * G::HIN;
+                constexpr int CPW = G::CIN / 8;                    // channels per producer warp
                 float* in_s = reinterpret_cast<float*>(in_raw);
+                float gch[CPW], bch[CPW];                          // issued now, needed after the statistics
+#pragma unroll
+                for (int i = 0; i < CPW; ++i) {
+                    gch[i] = __ldg(W + p.bn_g_off + c + 8 * i);
+                    bch[i] = __ldg(W + p.bn_b_off + c + 8 * i);
+                }
                 const float4* src = reinterpret_cast<const float4*>(p.y_in + f * (int64_t)NPIN * G::CIN);
                 for (int i = pt; i < NPIN * G::CIN / 4; i += CV_PROD) {
                     const float4 v = __ldg(src + i);
@@ -195,23 +202,40 @@ deepqn_conv_tc_kernel(const __grid_constant__ CUtensorMap map_w, const ConvParam
                     in_s[(c0 + 3) * G::LD + pos] = v.w;
                 }
                 asm volatile("bar.sync 1, 256;\n" ::: "memory");
-                for (int ch = c; ch < G::CIN; ch += 8) {           // one warp per channel, two-pass statistics
-                    float* row = in_s + ch * G::LD;
-                    float s = 0.f;
-                    for (int i = lane; i < NPIN; i += 32) s += row[i];
+                // one warp per channel, two-pass statistics; the channels of a warp are independent chains,
+                // unrolled so their shared-memory and shuffle latencies overlap
+                float mean[CPW], rstd[CPW];
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                    const float mean = s * (1.0f / NPIN);
+                for (int i = 0; i < CPW; ++i) {
+                    const float* row = in_s + (c + 8 * i) * G::LD;
+                    float s1 = 0.f;
+                    for (int q = lane; q < NPIN; q += 32) s1 += row[q];
+                    mean[i] = s1;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                    for (int i = 0; i < CPW; ++i) mean[i] += __shfl_xor_sync(0xffffffffu, mean[i], o);
+#pragma unroll
+                for (int i = 0; i < CPW; ++i) {
+                    const float* row = in_s + (c + 8 * i) * G::LD;
+                    mean[i] *= (1.0f / NPIN);
                     float qv = 0.f;
-                    for (int i = lane; i < NPIN; i += 32) {
-                        const float d = row[i] - mean;
+                    for (int q = lane; q < NPIN; q += 32) {
+                        const float d = row[q] - mean[i];
                         qv = fmaf(d, d, qv);
                     }
+                    rstd[i] = qv;
+                }
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) qv += __shfl_xor_sync(0xffffffffu, qv, o);
-                    const float rstd = 1.0f / sqrtf(qv * (1.0f / NPIN) + BN_EPS);
-                    const float g = __ldg(W + p.bn_g_off + ch), b = __ldg(W + p.bn_b_off + ch);
-                    for (int i = lane; i < NPIN; i += 32) row[i] = fmaxf(fmaf((row[i] - mean) * rstd, g, b), 0.f);
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                    for (int i = 0; i < CPW; ++i) rstd[i] += __shfl_xor_sync(0xffffffffu, rstd[i], o);
+#pragma unroll
+                for (int i = 0; i < CPW; ++i) {
+                    float* row = in_s + (c + 8 * i) * G::LD;
+                    const float rs = 1.0f / sqrtf(rstd[i] * (1.0f / NPIN) + BN_EPS);
+                    for (int q = lane; q < NPIN; q += 32) row[q] = fmaxf(fmaf((row[q] - mean[i]) * rs, gch[i], bch[i]), 0.f);
                 }
             }
             asm volatile("bar.sync 1, 256;\n" ::: "memory");
