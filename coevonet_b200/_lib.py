@@ -61,6 +61,8 @@ _SIGNATURES = {
     "cev_select_topk_f64": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "cev_es_perturb_f32": (c_int, [c_void_p, c_void_p, c_int, c_float, c_uint64, c_int, c_uint32,
                                    c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "cev_es_perturb_prefix_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_float, c_uint64, c_int, c_uint32,
+                                          c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "cev_es_update_f32": (c_int, [c_void_p, c_void_p, c_int, c_float, c_float, c_int64,
                                   c_uint64, c_int, c_uint32, c_int64, c_int64, c_void_p, c_void_p]),
     "cev_es_update_members_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_float, c_float,

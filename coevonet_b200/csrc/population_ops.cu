@@ -67,6 +67,30 @@ __global__ void __launch_bounds__(PT) es_perturb_kernel(
         *reinterpret_cast<float4*>(noise_out + r * pitch + (int64_t)j4 * 4) = make_float4(z[0], z[1], z[2], z[3]);
 }
 
+// K5 for rows whose perturbable parameters are a PREFIX of the row: DeepQN rows hold the conv / Linear
+// tensors first and the six BatchNorm vectors last (Atari/deepqn.py:158-172 get_perturbable_layers skips
+// them), so parameter j is perturbed iff j < d_pert.
+__global__ void __launch_bounds__(PT) es_perturb_prefix_kernel(
+    const float* __restrict__ theta, int64_t d_pert, int64_t d_total, int64_t pitch, float sigma,
+    uint32_t k0, uint32_t k1, uint32_t tag, uint32_t gen, int64_t row0, float* __restrict__ out) {
+    const int64_t r = blockIdx.x;
+    const int64_t j4 = (int64_t)blockIdx.y * PT + threadIdx.x;
+    if (j4 * 4 >= pitch) return;
+    const float4 pv = *reinterpret_cast<const float4*>(theta + j4 * 4);
+    float p[4] = {pv.x, pv.y, pv.z, pv.w};
+    if (j4 * 4 < d_pert) {
+        float z[4];
+        normal4(k0, k1, tag, gen, (uint32_t)(row0 + r), (uint32_t)j4, z);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (j4 * 4 + i < d_pert) p[i] = __fadd_rn(p[i], __fmul_rn(sigma, z[i]));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (j4 * 4 + i >= d_total) p[i] = 0.f;
+    __stcs(reinterpret_cast<float4*>(out + r * pitch + j4 * 4), make_float4(p[0], p[1], p[2], p[3]));
+}
+
 // ---------------------------------------------------------------------------
 // K6  ES update   (evolutionary_strategy.py:120-148)
 // delta = lr/(n*sigma) * sum_i (sigma*z_i) * F_i, noise regenerated from the
@@ -451,13 +475,33 @@ int cev_es_update_f32(cev_handle* h, const double* fitness, int in_dim, float si
     return check_cuda(cudaGetLastError(), "es_update kernels");
 }
 
+int cev_es_perturb_prefix_f32(cev_handle* h, const float* theta, int64_t d_pert, int64_t d_total, float sigma,
+                              uint64_t seed, int role, uint32_t gen, int64_t row0, int64_t n_rows, int64_t pitch,
+                              float* out, cev_stream stream) {
+    CEV_REQUIRE(h && theta && out, "es_perturb_prefix: null pointer");
+    CEV_REQUIRE(d_pert >= 0 && d_pert <= d_total && d_total <= pitch && pitch % 4 == 0 && pitch / 4 <= 0xFFFFFFFFll,
+                "es_perturb_prefix: need 0 <= d_pert <= d_total <= pitch, pitch a multiple of 4");
+    CEV_REQUIRE(aligned16(theta) && aligned16(out), "es_perturb_prefix: 16B alignment");
+    CEV_REQUIRE(row0 >= 0 && n_rows >= 0 && row0 + n_rows <= 0xFFFFFFFFll, "es_perturb_prefix: bad row range");
+    if (n_rows == 0) return CEV_OK;
+    uint32_t k0, k1;
+    split_seed(seed, k0, k1);
+    dim3 grid((unsigned)n_rows, (unsigned)((pitch / 4 + PT - 1) / PT));
+    es_perturb_prefix_kernel<<<grid, PT, 0, (cudaStream_t)stream>>>(theta, d_pert, d_total, pitch, sigma, k0, k1,
+                                                                   noise_tag(CEV_KIND_ES, role), gen, row0, out);
+    return check_cuda(cudaGetLastError(), "es_perturb_prefix_kernel");
+}
+
 int cev_es_update_members_f32(cev_handle* h, const double* fitness, const float* members, int64_t pitch,
                               const float* theta, int in_dim, float sigma, float lr, int64_t n_total,
                               int64_t n_rows, float* delta, cev_stream stream) {
     CEV_REQUIRE(h && fitness && members && theta && delta, "es_update_members: null pointer");
-    CEV_REQUIRE(in_dim == IN_ADV || in_dim == IN_GOOD, "es_update_members: in_dim must be 8 or 10");
     CEV_REQUIRE(n_total >= 1 && n_rows >= 0 && sigma > 0.f, "es_update_members: bad n/sigma");
-    CEV_REQUIRE(pitch == fc_pitch(in_dim), "es_update_members: rows must use the padded pitch cev_fc_pitch(in_dim)");
+    // in_dim 8 / 10: FCNetwork rows (pitch checked); in_dim 0: any row layout of `pitch` floats (DeepQN):
+    // the kernel is layout agnostic, unperturbed entries are copies of theta and contribute exact zeros
+    CEV_REQUIRE(in_dim == 0 || in_dim == IN_ADV || in_dim == IN_GOOD, "es_update_members: in_dim must be 0, 8 or 10");
+    CEV_REQUIRE(in_dim == 0 ? (pitch > 0 && pitch % 4 == 0) : pitch == fc_pitch(in_dim),
+                "es_update_members: rows must use the padded pitch (cev_fc_pitch / cev_dqn_pitch)");
     CEV_REQUIRE(aligned16(delta) && aligned16(members) && aligned16(theta), "es_update_members: 16B alignment");
     int n_split = (int)((n_rows + 31) / 32);
     if (n_split > 32) n_split = 32;

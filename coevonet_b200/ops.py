@@ -239,6 +239,22 @@ def es_perturb(theta, in_dim, sigma, seed, role, gen, row0, n_rows, *, out=None,
     return out
 
 
+def es_perturb_dqn(theta, c_in, n_actions, sigma, seed, role, gen, row0, n_rows, *, out=None):
+    """K5 for DeepQN rows: theta + sigma*N(0,1) on the conv / Linear parameters (a prefix of the row),
+    BatchNorm gamma / beta copied (``Atari/deepqn.py:158-172``)."""
+    dev = _need_cuda(theta, out)
+    pitch, total = layout.dqn_pitch(c_in, n_actions), layout.dqn_dim(c_in, n_actions)
+    d_pert = total - 2 * (32 + 64 + 64)
+    if theta.numel() < pitch:
+        raise _lib.CevError("es_perturb_dqn: theta must be a padded flat row")
+    if out is None:
+        out = torch.empty((n_rows, pitch), dtype=torch.float32, device=dev)
+    role_id = layout.ROLE_ID[role] if isinstance(role, str) else int(role)
+    check(_call("cev_es_perturb_prefix_f32", _h(dev), _ptr(theta), d_pert, total, float(sigma), int(seed), role_id,
+                int(gen), int(row0), int(n_rows), pitch, _ptr(out), _stream(dev)), "cev_es_perturb_prefix_f32")
+    return out
+
+
 def es_update(fitness, in_dim, sigma, lr, n_total, seed, role, gen, row0, *, out=None):
     """K6: delta fp32[pitch] = lr/(n_total*sigma) * sum_i (sigma z_i) fitness_i over the
     local members [row0, row0+len(fitness))."""
@@ -262,7 +278,7 @@ def es_update_members(fitness, members, theta, in_dim, sigma, lr, n_total, *, ou
     dev = _need_cuda(fitness, members, theta, out)
     if fitness.dtype != torch.float64 or fitness.shape[0] != members.shape[0]:
         raise _lib.CevError("es_update_members: fitness must be float64 [n_rows]")
-    pitch = layout.fc_pitch(in_dim)
+    pitch = layout.fc_pitch(in_dim) if in_dim else members.stride(0)      # in_dim 0: any row layout (DeepQN)
     if members.stride(0) != pitch or theta.numel() < pitch:
         raise _lib.CevError("es_update_members: members / theta must use the padded row pitch")
     if out is None:

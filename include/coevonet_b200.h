@@ -178,6 +178,16 @@ int cev_es_perturb_f32(cev_handle* h, const float* theta, int in_dim,
                        float* out, float* noise_out, cev_stream stream);
 
 /*
+ * K5 for rows whose perturbable parameters are a prefix of the row: DeepQN rows (conv / Linear tensors
+ * first, the six BatchNorm vectors last; Atari/deepqn.py:158-172 skips them).  out[r][j] = theta[j] +
+ * sigma * N(0,1) for j < d_pert, theta[j] for d_pert <= j < d_total, 0 up to the pitch; same Philox stream
+ * as cev_es_perturb_f32.
+ */
+int cev_es_perturb_prefix_f32(cev_handle* h, const float* theta, int64_t d_pert, int64_t d_total, float sigma,
+                              uint64_t seed, int role, uint32_t gen, int64_t row0, int64_t n_rows, int64_t pitch,
+                              float* out, cev_stream stream);
+
+/*
  * K6 -- ES fitness-weighted update.  Replaces compute_weight_update
  * (evolutionary_strategy.py:120-148): delta = lr/(n_total*sigma) *
  * sum_i (sigma*z_i) * fitness_i over members [row0, row0+n_rows), noise
@@ -195,7 +205,8 @@ int cev_es_update_f32(cev_handle* h, const double* fitness, int in_dim,
  * K6, from the materialised members: the same delta with sigma*z_i taken as members[i] - theta (the
  * rows cev_es_perturb_f32 wrote, pitch = cev_fc_pitch(in_dim)), i.e. the `noises` array of
  * compute_weight_update read back at HBM speed instead of regenerated on the ALU.  Differs from
- * cev_es_update_f32 by one rounding of the perturbation's add per term (1e-7 relative).
+ * cev_es_update_f32 by one rounding of the perturbation's add per term (1e-7 relative).  in_dim = 0 accepts
+ * any row layout of `pitch` floats (DeepQN rows): unperturbed entries equal theta and contribute zeros.
  */
 int cev_es_update_members_f32(cev_handle* h, const double* fitness, const float* members, int64_t pitch,
                               const float* theta, int in_dim, float sigma, float lr, int64_t n_total,

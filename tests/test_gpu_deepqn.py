@@ -87,3 +87,29 @@ def test_deepqn_module_dropin():
     srt = np.sort(want[0, 0])
     if srt[-1] - srt[-2] > 6e-3:
         assert net.determine_action(x[:1]) == int(np.argmax(want[0, 0]))
+
+
+def test_deepqn_es_perturb_and_update():
+    """BASELINE config 5 pieces: K5 on DeepQN rows (conv / Linear prefix perturbed with the Philox stream,
+    BatchNorm entries copied) and the layout-agnostic K6 from the materialised members."""
+    from coevonet_b200 import layout, ops
+    from oracle import philox
+    c_in, n_act, P, sigma, lr, seed, gen = 4, 18, 6, 0.05, 0.1, 99, 2
+    total, pitch = layout.dqn_dim(c_in, n_act), layout.dqn_pitch(c_in, n_act)
+    d_pert = total - 320
+    theta = torch.zeros(pitch, device="cuda")
+    theta[:total] = torch.from_numpy(weights.make_dqn_rows(1, c_in, n_act, 3, bn_jitter=0.1)[0]).cuda()
+    members = ops.es_perturb_dqn(theta, c_in, n_act, sigma, seed, "agent_0", gen, 10, P)
+    z = philox.normals(seed, philox.KIND_ES, philox.ROLE_ID["agent_0"], gen, np.arange(10, 10 + P), d_pert)
+    th = theta.cpu().numpy()
+    want = np.tile(th, (P, 1))
+    want[:, :d_pert] = th[:d_pert] + (np.float32(sigma) * z).astype(np.float32)
+    got = members.cpu().numpy()
+    np.testing.assert_allclose(got[:, :d_pert], want[:, :d_pert], rtol=0, atol=3e-6 * sigma + 1e-9)
+    assert np.array_equal(got[:, d_pert:], want[:, d_pert:])          # BatchNorm entries and padding untouched
+    fit = torch.randn(P, dtype=torch.float64, device="cuda")
+    delta = ops.es_update_members(fit, members, theta, 0, sigma, lr, P).cpu().numpy()
+    noise = got - th
+    ref = (np.float32(lr / (P * sigma)) * (noise.T.astype(np.float64) @ fit.cpu().numpy())).astype(np.float32)
+    np.testing.assert_allclose(delta, ref, rtol=0, atol=2e-5 * np.abs(ref).max())
+    assert np.all(delta[d_pert:] == 0)
