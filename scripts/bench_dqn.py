@@ -22,18 +22,20 @@ if world > 1:
     os.environ.setdefault("NCCL_DEBUG", "WARN")
     dist.init_process_group("nccl", device_id=dev)
 
-def timed(fn, n, warm=3):
+def timed(fn, n, warm=3, collective=True):
+    """Device time per call; with ``collective`` every rank must call it (barriers + max over ranks)."""
+    sync = collective and world > 1
     for _ in range(warm): fn()
-    if world > 1: dist.barrier()
+    if sync: dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(n): fn()
     e1.record()
-    if world > 1: dist.barrier()
+    if sync: dist.barrier()
     torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1) / n], dtype=torch.float64, device=dev)
-    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if sync: dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
 
 # ---- config 4: pong forward (C=4, A=6) ------------------------------------------------------------
@@ -43,7 +45,7 @@ if rank == 0:
     for P, B in ((2048, 1), (2048, 4)):
         members = (torch.rand((P, pitch), device=dev) - 0.5) * 0.05
         frames = ops.random_frames(1, (P, B, c_in, 84, 84), dev)
-        ms = timed(lambda: ops.deepqn_forward(members, frames, c_in, n_act), 5)
+        ms = timed(lambda: ops.deepqn_forward(members, frames, c_in, n_act), 5, collective=False)   # rank 0 only
         gb = (P * D * 4 + P * B * c_in * 7056) / 1e9
         print(json.dumps({"config": "4: pong_v3 DeepQN forward, synthetic frames", "members": P, "frames_per_member": B,
                           "ms": ms, "forwards_per_s": P * B / ms * 1e3, "algorithmic_GBps": gb / ms * 1e3,
