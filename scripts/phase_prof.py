@@ -5,15 +5,10 @@ from coevonet_b200 import _lib
 _lib.LIB_PATH = os.path.join(os.path.dirname(_lib.LIB_PATH), "libcoevonet_b200_prof.so")
 import numpy as np, torch
 from coevonet_b200 import layout, ops
-from oracle import weights
 lib = _lib.load()
 lib.cev_debug_profile.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.c_int]
-def pad(rows, in_dim):
-    out = np.zeros((rows.shape[0], layout.fc_pitch(in_dim)), dtype=np.float32)
-    out[:, :rows.shape[1]] = rows
-    return torch.from_numpy(out).cuda()
-theta = {"agent_0": pad(weights.make_fc_rows(1, 10, 1), 10), "agent_1": pad(weights.make_fc_rows(1, 10, 2), 10),
-         "adversary_0": pad(weights.make_fc_rows(1, 8, 3), 8)}
+theta = {"agent_0": ops.fc_init(10, 1, "agent_0", 0, 1, "cuda"), "agent_1": ops.fc_init(10, 2, "agent_1", 0, 1, "cuda"),
+         "adversary_0": ops.fc_init(8, 3, "adversary_0", 0, 1, "cuda")}
 names = ["tail(argmax/physics/obs)", "w1 wait", "layer1", "fc2 member", "fc2 streamed", "part reduce",
          "LN2 stats+dsmem", "cluster barrier 1", "normalise+logits+dsmem", "cluster barrier 2"]
 FLAGS = [int(x) for x in sys.argv[1:]] or [0]

@@ -4,16 +4,10 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from coevonet_b200 import layout, ops
-from oracle import weights
 
-def pad(rows, in_dim):
-    out = np.zeros((rows.shape[0], layout.fc_pitch(in_dim)), dtype=np.float32)
-    out[:, :rows.shape[1]] = rows
-    return torch.from_numpy(out).cuda()
 
-theta = {"agent_0": pad(weights.make_fc_rows(1, 10, 1), 10),
-         "agent_1": pad(weights.make_fc_rows(1, 10, 2), 10),
-         "adversary_0": pad(weights.make_fc_rows(1, 8, 3), 8)}
+theta = {"agent_0": ops.fc_init(10, 1, "agent_0", 0, 1, "cuda"), "agent_1": ops.fc_init(10, 2, "agent_1", 0, 1, "cuda"),
+         "adversary_0": ops.fc_init(8, 3, "adversary_0", 0, 1, "cuda")}
 shapes = [(1024, 16)] if len(sys.argv) < 2 else [tuple(int(v) for v in a.split("x")) for a in sys.argv[1:]]
 for P, E in shapes:
     members = ops.es_perturb(theta["agent_0"][0], 10, 0.05, 1, "agent_0", 0, 0, P)

@@ -1,6 +1,6 @@
 """Max abs error of the device normals vs the oracle's (development aid)."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from coevonet_b200 import layout, ops
 from oracle import philox

@@ -1,7 +1,7 @@
 """Lockstep K1 (variant 3) development check: parity vs the oracle on a small case, agreement with
 the cluster kernel at bench scale, and timing of both variants (development aid, not the bench)."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from coevonet_b200 import layout, ops
 from oracle import weights, mpe_env, rollout as orollout
