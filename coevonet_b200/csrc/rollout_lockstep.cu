@@ -1298,7 +1298,7 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
     // The two forwards of a world step are independent (same observations), use different pipes
     // (tensor vs FP32/HBM) and both end in a partial wave, so running them on two streams lets the
     // block scheduler fill one kernel's tail with the other's CTAs.  Measured: +4 % at 1024 members,
-    // -3 % at 4096 (the 227 KB opponent CTAs and 113 KB member CTAs cannot share an SM), so it is opt-in.
+    // -3 % at 4096 (the 227 KB opponent CTAs and 107 KB member CTAs cannot share an SM), so it is opt-in.
     const bool fork = want_fork && !h->timing_on;
     if (fork && !h->side_stream) {
         CEV_CUDA(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
