@@ -114,8 +114,6 @@ class _EngineBase:
         #: fill the partial waves and launch gaps of another's
         self.overlap_roles = bool(getattr(args, "overlap_roles", True)) and self.device.type == "cuda"
         self._role_streams = None
-        #: form each role's update on the role's stream right after its rollout (ES)
-        self.early_update = bool(getattr(args, "early_update", False))
         #: ES update from the materialised members (K6 as an HBM-bound read) instead of regenerating the
         #: noise from the Philox key (K6 as ALU work); both are within fp32 rounding of each other
         self.update_from_members = bool(getattr(args, "update_from_members", True))
@@ -297,7 +295,6 @@ class ESEngine(_EngineBase):
         self.rewards = {r: None for r in ROLES}
         self.diversity = {r: None for r in ROLES}
         self.last_delta = {r: None for r in ROLES}
-        self._delta_local = {r: None for r in ROLES}
 
     def sigma(self, role):
         a = self.args
@@ -350,14 +347,6 @@ class ESEngine(_EngineBase):
                 self.k1_events.append((e0, e1))
             slot = self._role_slot(out, role, limit)                  # [n_local, 1, E]
             self.rewards[role] = slot.mean(dim=(1, 2)).contiguous()
-            self._delta_local[role] = None
-            if self.early_update and not self.args.fitness_sharing:
-                # this rank's part of the update only needs this role's rewards: form it on the role's
-                # stream (theta itself is written later, in update(), once every rollout has read it)
-                fit_local = self.rewards[role].to(torch.float32).to(torch.float64).contiguous()
-                self._delta_local[role] = self.k.es_update(
-                    fit_local, in_dim, self.sigma(role), self.args.learning_rate, self.P, self.seed, role,
-                    self.gen, self.shard.row0)
 
         if self.overlap_roles and self.k1_events is None:
             if self._role_streams is None:
@@ -387,12 +376,11 @@ class ESEngine(_EngineBase):
                 self.diversity[role] = float(div)
                 fit_local = (fit_local.to(torch.float32) / (1 + div)).to(torch.float64)
             self.fitness[role] = self.comm.all_gather_rows(fit_local.contiguous(), self.shard)
-            delta, self._delta_local[role] = self._delta_local.get(role), None
-            if delta is None and self.update_from_members and hasattr(self.k, "es_update_members"):
+            if self.update_from_members and hasattr(self.k, "es_update_members"):
                 # sigma*z_i read back from the materialised members (HBM bound) instead of regenerated
                 delta = self.k.es_update_members(fit_local.contiguous(), self.members[role], self.theta[role],
                                                  in_dim, self.sigma(role), a.learning_rate, self.P)
-            elif delta is None:
+            else:
                 delta = self.k.es_update(fit_local.contiguous(), in_dim, self.sigma(role), a.learning_rate, self.P,
                                          self.seed, role, self.gen, self.shard.row0)
             self.comm.all_reduce_sum(delta)

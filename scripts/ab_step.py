@@ -21,6 +21,6 @@ def run(n=8):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
 for rep in range(2):
-    for ov, eu in ((False, False), (True, False), (True, True)):
-        eng.overlap_roles, eng.early_update = ov, eu
-        print(f"overlap_roles={ov} early_update={eu}: {run():.3f} ms per step", flush=True)
+    for ov in (False, True):
+        eng.overlap_roles = ov
+        print(f"overlap_roles={ov}: {run():.3f} ms per step", flush=True)
