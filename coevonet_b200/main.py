@@ -61,6 +61,10 @@ def parse_arguments(argv=None):
     p.add_argument("--device_init", action="store_true",
                    help="draw the GA founders on the device (Philox; same distribution as PyTorch's default "
                         "init) instead of building 3*P nn.Modules on the host; implied for population > 4096")
+    p.add_argument("--regenerate_noise", action="store_true",
+                   help="ES update: regenerate sigma*z from the Philox key (the reference's exact `noises` array) "
+                        "instead of reading it back as members - theta (faster, differs by the rounding of the "
+                        "perturbation's add)")
     p.add_argument("--play_discarded_hof_games", action="store_true",
                    help="GA, reference_compat: also simulate the hof_size-1 games per member whose reward the "
                         "reference overwrites (they never reach the fitness; skipped by default)")
@@ -119,6 +123,7 @@ class Args:
             self.init_states = "device"
         self.seed = a.seed
         self.play_discarded_hof_games = a.play_discarded_hof_games
+        self.update_from_members = not a.regenerate_noise
         self.plots = not a.no_plots
 
     def print_attributes(self, args=None):

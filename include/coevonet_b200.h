@@ -205,7 +205,8 @@ int cev_es_update_f32(cev_handle* h, const double* fitness, int in_dim,
  * K6, from the materialised members: the same delta with sigma*z_i taken as members[i] - theta (the
  * rows cev_es_perturb_f32 wrote, pitch = cev_fc_pitch(in_dim)), i.e. the `noises` array of
  * compute_weight_update read back at HBM speed instead of regenerated on the ALU.  Differs from
- * cev_es_update_f32 by one rounding of the perturbation's add per term (1e-7 relative).  in_dim = 0 accepts
+ * cev_es_update_f32 by one rounding of the perturbation's add per term (at most ulp(theta)/2 absolute:
+ * about 1e-6 of sigma*z at |theta| ~ 1, sigma = 0.05 -- the same rounding the rollout's members carry).  in_dim = 0 accepts
  * any row layout of `pitch` floats (DeepQN rows): unperturbed entries equal theta and contribute zeros.
  */
 int cev_es_update_members_f32(cev_handle* h, const double* fitness, const float* members, int64_t pitch,

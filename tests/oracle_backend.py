@@ -108,6 +108,15 @@ def es_update(fitness, in_dim, sigma, lr, n_total, seed, role, gen, row0, *, out
     return torch.from_numpy(delta)
 
 
+def es_update_members(fitness, members, theta, in_dim, sigma, lr, n_total, *, out=None):
+    """K6 from the materialised members: sigma*z_i taken as members[i] - theta (the engine's default)."""
+    pitch = members.shape[1]
+    noise = (members.numpy() - theta.numpy()[:pitch]).astype(np.float32)
+    f = fitness.numpy().astype(np.float32)
+    coef = np.float32(lr / (n_total * sigma))
+    return torch.from_numpy((coef * (noise.T @ f)).astype(np.float32))
+
+
 def axpy(a, x, y):
     y.add_(x, alpha=a)
     return y
