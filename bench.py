@@ -51,9 +51,12 @@ def _args_bag(P):
 def _config(n_gpus):
     return {"workload": "Co-ES simple_adversary_v3 population evaluation (BASELINE configs[1])",
             "population_per_gpu": P_PER_GPU, "population": P_PER_GPU * n_gpus, "envs_per_member": ENVS,
-            "roles": 3, "cycles_per_episode": CYCLES, "noise": "Philox4x32-10 regenerated from seed",
+            "roles": 3, "cycles_per_episode": CYCLES,
+            "noise": "Philox4x32-10: members materialised from the seed by K5 every generation (never stored "
+                     "across generations); the update reads sigma*z back as members - theta (K6, members form)",
             "step": "one generation: 3 x (perturb, rollout, update) + 10 eval games; the three roles' "
-                    "evaluations run on three CUDA streams",
+                    "evaluations run on three CUDA streams, the eval games on a fourth; no host round trip "
+                    "inside a generation (sigma / reward history / status live on the device)",
             "env_step_definition": "world step (3 agent env.step calls); agent-steps/s = 3 x value",
             "cache": "inputs larger than L2 (3 x 1024 member rows = 1.7 GB per GPU vs 126 MB L2)",
             "parallelism": f"population sharded over {n_gpus} GPU(s)"}
@@ -150,6 +153,17 @@ def cpu_baseline_block(budget_s=12.0):
                       f"oracle/serial_port.py) in {wall:.1f} s; the reference is single-process"}
 
 
+def parity_block(dev):
+    """Member-level parity of the bench workload against the oracle (the checker, never the thing
+    measured): the fraction of sampled config-2 members whose fitness is within 1e-4 relative, and the
+    episode fork count.  Runs in the cpu_baseline leg (rank 0, N = 1)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_gpu_parity_r2 import member_match_stats
+    st = member_match_stats(n_sample=128, P=P_PER_GPU, E=ENVS)
+    st["checked_against"] = "oracle/rollout.py on 3 x 128 full members (16 episodes each) of one generation"
+    return st
+
+
 def run_reference_arm(ns):
     """The reference's CPU implementation of the path (port; /root/reference does not
     travel to the GPU box), all host cores, each step a bounded sample."""
@@ -182,6 +196,63 @@ def run_reference_arm(ns):
 # ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
+def _lib_device_info(local):
+    from coevonet_b200 import _lib
+    return _lib.device_info(local)
+
+
+class _NoComm:
+    """A single-rank view inside a multi-rank job (the reference run of _sharded_equals_single)."""
+    enabled, rank, world, group = False, 0, 1, None
+
+    def all_gather_rows(self, local, shard):
+        return local
+
+    def all_reduce_sum(self, t):
+        return t
+
+    def all_reduce_max(self, t):
+        return t
+
+    def broadcast0(self, t):
+        return t
+
+
+def _sharded_equals_single(engine, layout, FCNetwork, args, dev, comm, rank):
+    """One generation of the GLOBAL population, sharded over the ranks, against the same generation run by
+    rank 0 alone (evolutionary_strategy.py:236-265): member rewards must be bit-identical (Philox counters use
+    global member ids, every rank runs the K1 variant chosen for the global shape); the all-reduced delta may
+    differ from the single-rank sum by fp32 summation order only."""
+    import torch
+    import torch.distributed as dist
+    torch.manual_seed(0)
+    theta = {r: FCNetwork(layout.OBS_DIM[r], 5, "float32").flat_row() for r in ROLES}
+    sh = engine.ESEngine(args, dev, theta, comm=comm)
+    sh.evaluate()
+    sh.update()
+    rewards = torch.stack([comm.all_gather_rows(sh.rewards[r], sh.shard) for r in ROLES])
+    delta = sh.delta_cat.clone()
+    res = None
+    if rank == 0:
+        single = engine.ESEngine(args, dev, theta, comm=_NoComm())
+        single.evaluate()
+        single.update()
+        r1 = torch.stack([single.rewards[r] for r in ROLES])
+        scale = float(single.delta_cat.abs().max())
+        diff = float((single.delta_cat - delta).abs().max())
+        same = bool(torch.equal(r1, rewards))
+        res = {"equal": bool(same and diff <= 1e-5 * scale), "rewards_bit_identical": same,
+               "members_compared": int(r1.numel()), "delta_max_abs_diff": diff, "delta_scale": scale,
+               "generations": 1, "k1_variant": int(sh.variant),
+               "note": "rank 0 re-runs the whole global population alone; delta differs by the summation order of "
+                       "the all-reduce only"}
+        del single
+    del sh
+    torch.cuda.empty_cache()
+    dist.barrier()
+    return res
+
+
 def run_gpu_arm(ns):
     import numpy as np
     import torch
@@ -220,7 +291,7 @@ def run_gpu_arm(ns):
 
     # ---- device-resident throughput (`value`) --------------------------------
     for _ in range(ns.warmup):
-        eng.step()
+        eng.step(sync=False)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -230,9 +301,10 @@ def run_gpu_arm(ns):
     barrier()
     e0.record()
     for _ in range(ns.steps):
-        eng.step()
+        eng.step(sync=False)
     e1.record()
     barrier()
+    eng.check_status()
     clocks = sampler.stop() if rank == 0 else None
     launches = ops.launch_count - launches0
     ms_total = e0.elapsed_time(e1)
@@ -249,7 +321,7 @@ def run_gpu_arm(ns):
     barrier()
     r0.record()
     for _ in range(roof_steps):
-        eng.step()
+        eng.step(sync=False)
     r1.record()
     barrier()
     ms_serial = r0.elapsed_time(r1)
@@ -279,32 +351,57 @@ def run_gpu_arm(ns):
         for r in ROLES:
             eng.theta[r].copy_(theta_host[r], non_blocking=True)
         init_dev = {r: init_host[r].to(dev, non_blocking=True) for r in ROLES}
-        eng.step(init_by_role=init_dev)
+        eng.step(init_by_role=init_dev, sync=False)
         for r in ROLES:
             fit_host[r].copy_(eng.rewards[r], non_blocking=True)
             theta_host[r].copy_(eng.theta[r], non_blocking=True)
-        torch.cuda.synchronize()
+        torch.cuda.synchronize()          # the caller holds the generation's results on the host
 
     h2d = sum(init_host[r].numel() * 8 + theta_host[r].numel() * 4 for r in ROLES)
     d2h = sum(fit_host[r].numel() * 8 + theta_host[r].numel() * 4 for r in ROLES)
-    e2e_steps = max(1, min(ns.steps, 5))
-    e2e_step()
+    e2e_steps = ns.steps                  # the full --steps, host clock
+    for _ in range(min(ns.warmup, 2)):
+        e2e_step()
     barrier()
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    g0.record()
+    t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_step()
-    g1.record()
     barrier()
-    e2e_ms = g0.elapsed_time(g1)          # device clock; the per-step host waits fall inside the bracket
+    e2e_ms = (time.perf_counter() - t0) * 1e3
     t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = steps_per_gen * e2e_steps / (float(t.item()) * 1e-3)
 
+    # ---- N > 1: the sharded run against a single-rank run of the same GLOBAL population ----------
+    sharded = None
+    if world > 1:
+        sharded = _sharded_equals_single(engine, layout, FCNetwork, args, dev, comm, rank)
+
+    # ---- secondary configs / kernels (bench_secondary.py) -------------------------------------
+    secondary = None
+    if not ns.no_secondary:
+        import bench_secondary as bs
+        peaks_s, peaks_src_s = _measured_peaks()
+        torch.cuda.empty_cache()
+        secondary = {}
+        if world == 1:
+            secondary["kernels"] = bs.kernel_rooflines(dev, float(peaks_s["hbm_gbs"]), peaks_src_s)
+            secondary["config4_dqn_forward"] = bs.config4_dqn_forward(
+                dev, float(peaks_s["hbm_gbs"]),
+                float(peaks_s.get("bf16_tflops_sustained", peaks_s["bf16_tflops"])) / 2.0)
+            torch.cuda.empty_cache()
+        secondary["config3_ga"] = bs.config3_ga(dev, comm)
+        torch.cuda.empty_cache()
+        secondary["config5_dqn_es"] = bs.config5_dqn_es(dev, comm)
+        torch.cuda.empty_cache()
+
     if rank == 0:
         peaks, peaks_src = _measured_peaks()
         fp32_peak = max(ops.fp32_peak(dev, 0), ops.fp32_peak(dev, 1))
+        n_sm, _ = _lib_device_info(local)
+        sm_max = (clocks or {}).get("sm_max_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+        fp32_theory = n_sm * 128 * 2 * sm_max * 1e6 / 1e12          # 128 FMA lanes per SM per clock
         k1_avg_ms = float(np.mean(k1_ms))
         k1_flop = n_local * ENVS * CYCLES * FLOP_PER_WORLD_STEP
         traffic = _k1_traffic()
@@ -321,7 +418,9 @@ def run_gpu_arm(ns):
                     "k1_algorithmic_flop_per_call": k1_flop,
                     "fp32_peak_tflops": fp32_peak,
                     "fp32_peak_source": "FP32 FMA-pipe peak measured live by cev_fp32_peak (MEASURED_PEAKS.json "
-                                        "has no FP32 figure)"}
+                                        "has no FP32 figure)",
+                    "fp32_peak_theoretical_tflops": fp32_theory,
+                    "fp32_peak_theoretical_def": f"{n_sm} SMs x 128 FMA lanes x 2 x {sm_max:.0f} MHz"}
         if k1_variant == 3 and member_n > 0:
             # dominant kernel: ls_member_kernel, one launch per world step; it streams every member row once
             # per launch (algorithmic bytes = rows x D x 4, D averaged over the three roles' launches)
@@ -332,9 +431,22 @@ def run_gpu_arm(ns):
             achieved = alg_bytes / (member_us * 1e-6) / 1e9
             member_flop = n_local * ENVS * (2 * 274944 + 272896) / 3.0
             opp_flop = 2.0 * n_local * ENVS * 2 * 512 * 256          # fc2 of the two opponent seats
+            hbm_floor_us = alg_bytes / (hbm_peak * 1e9) * 1e6
+            fp32_floor_us = member_flop / (fp32_peak * 1e12) * 1e6
             roof = {"kernel": "ls_member_kernel (K1 lockstep, member forward; one launch per world step)",
                     "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                     "frac": achieved / hbm_peak,
+                    "floors": {
+                        "per_launch_hbm_us": hbm_floor_us, "per_launch_fp32_us": fp32_floor_us,
+                        "per_launch_fp32_theoretical_us": member_flop / (fp32_theory * 1e12) * 1e6,
+                        "per_rollout_hbm_bytes_streamed": alg_bytes * CYCLES,
+                        "per_rollout_hbm_bytes_if_rows_stayed_on_chip": alg_bytes,
+                        "note": "the lockstep form re-streams every member row once per world step (25x the "
+                                "once-per-rollout bytes of SURVEY.md 8d): that is a design choice, not the "
+                                "algorithm.  Per launch the HBM floor is above the FP32 floor, so `bound` is "
+                                "hbm; against the FP32 pipe the kernel is at fp32_frac.  The kernel sits "
+                                "between both floors because ~40 % of a CTA's life is outside the saturated "
+                                "fc2 loop (profiles/README.md)."},
                     "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks_src})",
                     "us_per_launch": member_us, "launches_timed": member_n,
                     "share_of_step": member_ms / ms_serial,
@@ -372,8 +484,14 @@ def run_gpu_arm(ns):
             "gpu_launches": launches,
             "clocks": clocks,
         }
+        if sharded is not None:
+            line["sharded_equals_single"] = sharded["equal"]
+            line["sharded_check"] = sharded
+        if secondary is not None:
+            line["secondary"] = secondary
         if world == 1 and not ns.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_block()
+            line["parity"] = parity_block(dev)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -387,6 +505,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--no-secondary", dest="no_secondary", action="store_true",
+                    help="skip the secondary configs / per-kernel rooflines (bench_secondary.py)")
     ns = ap.parse_args()
     if ns.impl == "reference":
         return run_reference_arm(ns)

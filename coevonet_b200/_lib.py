@@ -21,6 +21,9 @@ SEAT = {"adversary_0": 0, "agent_0": 1, "agent_1": 2}
 KIND_ES, KIND_GA, KIND_ENV, KIND_FRAMES = 0, 1, 2, 3
 INIT_STATE_DIM = 11
 ROLLOUT_OUT_DIM = 4
+ORDER_STABLE_DESC, ORDER_REFERENCE = 0, 1
+#: slots of the device generation state (CEV_GS_* in include/coevonet_b200.h)
+GS_GEN, GS_SIGMA, GS_BEST, GS_STALE, GS_STOP, GS_STOP_GEN, GS_LAST_EVAL, GS_HIST = 0, 1, 4, 7, 10, 11, 12, 16
 
 
 class RolloutCfg(Structure):
@@ -46,6 +49,10 @@ _SIGNATURES = {
                                     c_void_p, c_int64, c_void_p, c_int64, c_int,
                                     c_void_p, c_int, c_int, POINTER(RolloutCfg),
                                     c_void_p, c_void_p, c_void_p]),
+    "cev_mpe_rollout_trace_f32": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64,
+                                          c_void_p, c_int64, c_void_p, c_int64, c_int,
+                                          c_void_p, c_int, c_int, POINTER(RolloutCfg),
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cev_mpe_rollout_plan": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]),
     "cev_kernel_timing_enable": (c_int, [c_void_p, c_int]),
     "cev_kernel_timing_read": (c_int, [c_void_p, c_int, POINTER(c_double), POINTER(c_int)]),
@@ -54,19 +61,24 @@ _SIGNATURES = {
                                             POINTER(RolloutCfg), c_void_p, c_void_p, c_void_p]),
     "cev_fc_forward_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64,
                                    c_void_p, c_void_p, c_void_p, c_void_p]),
-    "cev_ga_repopulate_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_float,
+    "cev_ga_repopulate_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_float, c_void_p,
                                       c_uint64, c_int, c_uint32, c_int64, c_int64,
                                       c_void_p, c_void_p, c_void_p]),
-    "cev_gather_rows_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
-    "cev_select_topk_f64": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
-    "cev_es_perturb_f32": (c_int, [c_void_p, c_void_p, c_int, c_float, c_uint64, c_int, c_uint32,
+    "cev_gather_rows_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int64, c_int64, c_void_p,
+                                    c_void_p]),
+    "cev_select_topk_f64": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    "cev_es_perturb_f32": (c_int, [c_void_p, c_void_p, c_int, c_float, c_void_p, c_uint64, c_int, c_uint32,
                                    c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
-    "cev_es_perturb_prefix_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_float, c_uint64, c_int, c_uint32,
-                                          c_int64, c_int64, c_int64, c_void_p, c_void_p]),
-    "cev_es_update_f32": (c_int, [c_void_p, c_void_p, c_int, c_float, c_float, c_int64,
+    "cev_es_perturb_prefix_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p, c_uint64, c_int,
+                                          c_uint32, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
+    "cev_es_update_f32": (c_int, [c_void_p, c_void_p, c_int, c_float, c_void_p, c_float, c_int64,
                                   c_uint64, c_int, c_uint32, c_int64, c_int64, c_void_p, c_void_p]),
-    "cev_es_update_members_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_float, c_float,
-                                          c_int64, c_int64, c_void_p, c_void_p]),
+    "cev_es_update_members_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_float, c_void_p,
+                                          c_float, c_int64, c_int64, c_void_p, c_void_p]),
+    "cev_weight_stats_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
+    "cev_generation_state_doubles": (c_int, [c_int]),
+    "cev_generation_end_f64": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_double,
+                                       c_double, c_int, c_double, c_int, c_void_p]),
     "cev_axpy_f32": (c_int, [c_void_p, c_float, c_void_p, c_void_p, c_int64, c_void_p]),
     "cev_diversity_dist_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int,
                                        c_void_p, c_void_p]),

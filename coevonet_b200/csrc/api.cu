@@ -38,7 +38,7 @@ int cev_create(int device, cev_handle** out) {
     int count = 0;
     CEV_CUDA(cudaGetDeviceCount(&count));
     CEV_REQUIRE(device >= 0 && device < count, "cev_create: device %d out of range (%d devices)", device, count);
-    CEV_CUDA(cudaSetDevice(device));
+    DeviceGuard guard(device);          // the caller's current device is restored on return
     cudaDeviceProp prop;
     CEV_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) {
@@ -69,6 +69,7 @@ int cev_create(int device, cev_handle** out) {
 
 int cev_destroy(cev_handle* h) {
     if (!h) return CEV_OK;
+    CEV_GUARD(h);
     if (h->workspace) cudaFree(h->workspace);
     if (h->opp_workspace) cudaFree(h->opp_workspace);
     if (h->ls_workspace) cudaFree(h->ls_workspace);
@@ -137,6 +138,7 @@ int cev_mpe_rollout_f32(cev_handle* h, int member_seat, const float* members, in
                 "mpe_rollout: opponent pitch too small / not a multiple of 4");
     CEV_REQUIRE(aligned16(members) && aligned16(opp_a) && aligned16(opp_b), "mpe_rollout: rows must be 16B aligned");
     if (P == 0) return CEV_OK;
+    CEV_GUARD(h);
     cudaStream_t st = (cudaStream_t)stream;
     const int variant = rollout_plan(h, P, K, E, cfg->variant);
     if (variant >= 2) {
@@ -180,6 +182,46 @@ int cev_mpe_rollout_f32(cev_handle* h, int member_seat, const float* members, in
     return launch_rollout_generic(h, g, st);
 }
 
+int cev_mpe_rollout_trace_f32(cev_handle* h, int member_seat, const float* members, int P, int64_t member_pitch,
+                              const float* opp_a, int64_t opp_a_pitch, const float* opp_b, int64_t opp_b_pitch, int K,
+                              const double* init, int init_shared, int E, const cev_rollout_cfg* cfg,
+                              const int32_t* forced_actions, float* logits_out, int32_t* actions_out, double* out,
+                              int32_t* status, cev_stream stream) {
+    CEV_REQUIRE(h && members && opp_a && opp_b && init && out, "mpe_rollout_trace: null pointer");
+    CEV_REQUIRE(member_seat >= 0 && member_seat <= 2, "mpe_rollout_trace: member_seat must be 0..2");
+    CEV_REQUIRE(P >= 1 && K >= 1 && E >= 1, "mpe_rollout_trace: need P, K, E >= 1");
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    const int other[2] = {member_seat == 0 ? 1 : 0, member_seat == 2 ? 1 : 2};
+    CEV_REQUIRE(member_pitch >= fc_offsets(seat_in_dim(member_seat)).total && member_pitch % 4 == 0 &&
+                    opp_a_pitch >= fc_offsets(seat_in_dim(other[0])).total && opp_a_pitch % 4 == 0 &&
+                    opp_b_pitch >= fc_offsets(seat_in_dim(other[1])).total && opp_b_pitch % 4 == 0,
+                "mpe_rollout_trace: pitch too small / not a multiple of 4");
+    CEV_REQUIRE(aligned16(members) && aligned16(opp_a) && aligned16(opp_b), "mpe_rollout_trace: rows must be 16B aligned");
+    CEV_GUARD(h);
+    ClusterParams p{};
+    p.members = members;
+    p.member_pitch = member_pitch;
+    p.P = P;
+    p.opp[0] = opp_a;
+    p.opp[1] = opp_b;
+    p.opp_pitch[0] = opp_a_pitch;
+    p.opp_pitch[1] = opp_b_pitch;
+    p.K = K;
+    p.member_seat = member_seat;
+    p.init = init;
+    p.init_shared = init_shared;
+    p.E = E;
+    p.out = out;
+    p.status = status;
+    p.n_cycles = cfg->n_cycles;
+    p.pos_first = cfg->integrate_pos_first;
+    p.trace_forced = forced_actions;
+    p.trace_logits = logits_out;
+    p.trace_actions = actions_out;
+    return launch_rollout_lockstep(h, p, (cudaStream_t)stream);
+}
+
 int cev_mpe_rollout_plan(cev_handle* h, int P, int K, int E, int n_cycles, int variant, int* variant_used,
                          int* n_launches) {
     CEV_REQUIRE(h != nullptr, "mpe_rollout_plan: null handle");
@@ -192,6 +234,7 @@ int cev_mpe_rollout_plan(cev_handle* h, int P, int K, int E, int n_cycles, int v
 
 int cev_kernel_timing_enable(cev_handle* h, int on) {
     CEV_REQUIRE(h != nullptr, "kernel_timing_enable: null handle");
+    CEV_GUARD(h);
     if (on && !h->timing_ev[0]) {
         for (int k = 0; k < 2; ++k) {
             h->timing_ev[k] = new cudaEvent_t[2 * CEV_TIMING_MAX];
@@ -205,6 +248,7 @@ int cev_kernel_timing_enable(cev_handle* h, int on) {
 
 int cev_kernel_timing_read(cev_handle* h, int which, double* total_ms, int* n_launches) {
     CEV_REQUIRE(h != nullptr && (which == 0 || which == 1), "kernel_timing_read: bad arguments");
+    CEV_GUARD(h);
     double tot = 0.0;
     const int n = h->timing_n[which];
     for (int i = 0; i < n; ++i) {
@@ -232,6 +276,7 @@ int cev_mpe_rollout_indexed_f32(cev_handle* h, const float* w_adv, int64_t adv_p
                     a1_pitch % 4 == 0,
                 "mpe_rollout_indexed: pitch too small / not a multiple of 4");
     CEV_REQUIRE(aligned16(w_adv) && aligned16(w_a0) && aligned16(w_a1), "mpe_rollout_indexed: rows must be 16B aligned");
+    CEV_GUARD(h);
     GenericParams g{};
     g.w[0] = w_adv;
     g.w[1] = w_a0;
@@ -260,6 +305,7 @@ int cev_fc_forward_f32(cev_handle* h, const float* rows, int64_t pitch, int in_d
     CEV_REQUIRE(in_dim == IN_ADV || in_dim == IN_GOOD, "fc_forward: in_dim must be 8 or 10");
     CEV_REQUIRE(pitch >= fc_offsets(in_dim).total && pitch % 4 == 0 && aligned16(rows),
                 "fc_forward: bad pitch / alignment");
+    CEV_GUARD(h);
     return launch_fc_forward(h, rows, pitch, in_dim, idx, obs, N, logits, actions, status, (cudaStream_t)stream);
 }
 

@@ -65,6 +65,22 @@ int check_cuda(cudaError_t e, const char* what);
         if (_rc != 0) return _rc;                             \
     } while (0)
 
+// Every entry point runs on the handle's device, whatever the caller's current device is, and leaves
+// the caller's current device untouched (a process that drives several GPUs keeps torch's device).
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define CEV_GUARD(h) ::cev::DeviceGuard _cev_device_guard((h)->device)
+
 #define CEV_REQUIRE(cond, ...)                                \
     do {                                                      \
         if (!(cond)) {                                        \
@@ -199,20 +215,56 @@ __host__ __device__ __forceinline__ U4 philox4x32_10(U4 c, uint32_t k0, uint32_t
     return c;
 }
 
+// The ten round keys of a launch, precomputed on the host: as a kernel parameter they sit in the constant
+// bank and cost the noise kernels no per-thread key-schedule adds.
+struct PhiloxKeys {
+    uint32_t a[10], b[10];
+};
+__host__ __device__ __forceinline__ PhiloxKeys philox_keys(uint32_t k0, uint32_t k1) {
+    PhiloxKeys k;
+    for (int r = 0; r < 10; ++r) {
+        k.a[r] = k0 + (uint32_t)r * 0x9E3779B9u;
+        k.b[r] = k1 + (uint32_t)r * 0xBB67AE85u;
+    }
+    return k;
+}
+__device__ __forceinline__ U4 philox4x32_10(U4 c, const PhiloxKeys& k) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)M0 * c.x, p1 = (uint64_t)M1 * c.z;
+        c = U4{(uint32_t)(p1 >> 32) ^ c.y ^ k.a[r], (uint32_t)p1, (uint32_t)(p0 >> 32) ^ c.w ^ k.b[r], (uint32_t)p0};
+    }
+    return c;
+}
+
 __device__ __forceinline__ float u01(uint32_t x) {
     // (0,1]: x * 2^-32 + 2^-33 ; the scaling is exact so FMA contraction is harmless
     return __fmaf_rn(__uint2float_rn(x), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
 }
 
-// Box-Muller with the sine / cosine on the SFU (MUFU.SIN / MUFU.COS, absolute error 2^-21.2 on [-pi, pi]):
-// the normals of K3/K5/K6 are ALU bound (141 M per ES role and generation) and sincospif was the largest
-// part of that cost.  The logarithm stays libm-accurate (near u1 = 1 the SFU log2 has no relative accuracy
-// left and r = sqrt(-2 log u1) would be off by up to 5e-4).  Absolute error of a normal vs the fp64-accurate
-// value: a few 1e-6; every consumer regenerates noise with this same function, so the streams agree.
+// Box-Muller on the SFU.  The normals of K3/K5/K6 are ALU bound (141 M per ES role and generation), so every
+// transcendental is one MUFU instruction with the accuracy argued below (absolute error of a normal vs the
+// fp64-accurate value: <= 3e-6 for |z| <= 5; tests/test_gpu_population.py states the bound); every consumer
+// regenerates noise with this same function, so the streams agree bit for bit.
+//  * r^2 = -2 ln u1: MUFU.LG2 (__log2f: absolute error 2^-22 on [0.5, 2], 2 ulp elsewhere) times ln 2 -- except
+//    near u1 = 1, where the result is near 0 and an absolute error is a large RELATIVE one (r would be off by
+//    up to 5e-4): there t = 1 - u1 is exact (Sterbenz) and -ln(1 - t) = t + t^2/2 + ... + t^5/5 is good to
+//    t^5/6 < 6e-9 relative for t < 1/32.  Outside that window |ln u1| >= 0.0317, so dr <= 2^-22 ln2 / r <= 7e-7.
+//  * r = sqrt.approx (MUFU.SQRT, relative error 2^-23).
+//  * sine / cosine: MUFU.SIN / MUFU.COS are accurate on [-pi, pi] (absolute error 2^-21.4): evaluate at
+//    2 pi u2 - pi and flip both signs.
+__device__ __forceinline__ float neg2_log_u(float u) {
+    const float t = 1.0f - u;
+    const float ser = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 0.2f, 0.25f), 0.33333334f), 0.5f), 1.0f);
+    const float lg = -0.6931471805599453f * __log2f(u);
+    return 2.0f * (t < 0.03125f ? ser : lg);
+}
+
 __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float& z0, float& z1) {
     const float u1 = u01(xa), u2 = u01(xb);
-    const float r = sqrtf(-2.0f * logf(u1));     // libm-accurate: __logf loses all relative accuracy near u1 = 1
-    // MUFU.SIN / MUFU.COS are accurate on [-pi, pi]: evaluate at 2 pi u - pi and flip both signs
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;\n" : "=f"(r) : "f"(neg2_log_u(u1)));
     float s, c;
     __sincosf(6.283185307179586f * (u2 - 0.5f), &s, &c);
     z0 = -(r * c);
@@ -220,9 +272,9 @@ __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float& z0, 
 }
 
 // four standard normals for flat parameter indices 4*j4 .. 4*j4+3 of `member`
-__device__ __forceinline__ void normal4(uint32_t k0, uint32_t k1, uint32_t tag, uint32_t gen,
+__device__ __forceinline__ void normal4(const PhiloxKeys& keys, uint32_t tag, uint32_t gen,
                                         uint32_t member, uint32_t j4, float z[4]) {
-    const U4 r = philox4x32_10(U4{j4, member, gen, tag}, k0, k1);
+    const U4 r = philox4x32_10(U4{j4, member, gen, tag}, keys);
     box_muller(r.x, r.y, z[0], z[1]);
     box_muller(r.z, r.w, z[2], z[3]);
 }
@@ -286,6 +338,10 @@ struct ClusterParams {
     double* out;
     int32_t* status;
     int n_cycles, pos_first;
+    // parity instrumentation of the lockstep form (cev_mpe_rollout_trace_f32), null in production
+    const int32_t* trace_forced;  // [n_cycles][3][N] actions to replay
+    float* trace_logits;          // [n_cycles][3][N][5]
+    int32_t* trace_actions;       // [n_cycles][3][N] the networks' own decisions
 };
 int launch_rollout_generic(cev_handle* h, const GenericParams& p, cudaStream_t stream);
 int launch_rollout_cluster(cev_handle* h, const ClusterParams& p, cudaStream_t stream);

@@ -294,6 +294,7 @@ extern "C" int cev_deepqn_forward(cev_handle* h, const float* members, int P, in
     CEV_REQUIRE((reinterpret_cast<uintptr_t>(members) & 15u) == 0 && (reinterpret_cast<uintptr_t>(frames) & 15u) == 0,
                 "deepqn_forward: rows and frames must be 16B aligned");
     if (P == 0) return CEV_OK;
+    CEV_GUARD(h);
     // activation scratch (stays in L2 between the layer phases of a member)
     const size_t per = (size_t)P * B;
     const size_t need = per * (12800 + 5184 + 3136 + 3136) * sizeof(float);

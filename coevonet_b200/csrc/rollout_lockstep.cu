@@ -137,6 +137,10 @@ struct LsEnvParams {
     int K, E, init_shared, pos_first, last;
     const double* init;
     double* out;
+    // parity instrumentation (cev_mpe_rollout_trace_f32; null in production): replay these actions
+    // instead of the networks' (teacher forcing), and record the networks' own decisions
+    const int32_t* forced;   // this cycle's [3][N]
+    int32_t* act_out;        // this cycle's [3][N]
 };
 
 __global__ void __launch_bounds__(256) ls_init_kernel(const LsEnvParams p) {
@@ -167,7 +171,17 @@ __global__ void __launch_bounds__(256) ls_env_step_kernel(const LsEnvParams p) {
     if (ep >= p.N) return;
     EnvState s;
     ls_load_state(p.b, p.N, ep, s);
-    const int act[3] = {p.b.act[ep], p.b.act[p.N + ep], p.b.act[2 * p.N + ep]};
+    int act[3] = {p.b.act[ep], p.b.act[p.N + ep], p.b.act[2 * p.N + ep]};
+    if (p.act_out) {
+        p.act_out[ep] = act[0];
+        p.act_out[p.N + ep] = act[1];
+        p.act_out[2 * p.N + ep] = act[2];
+    }
+    if (p.forced) {
+        act[0] = p.forced[ep];
+        act[1] = p.forced[p.N + ep];
+        act[2] = p.forced[2 * p.N + ep];
+    }
     const float g = fminf(p.b.gap[ep], fminf(p.b.gap[p.N + ep], p.b.gap[2 * p.N + ep]));
     double rg, ra;
     env_step(s, act, p.pos_first != 0, rg, ra);
@@ -308,6 +322,7 @@ struct LsMemberParams {
     int32_t* act;         // this seat's [N]
     float* gap;
     int32_t* status;
+    float* logits;        // this seat's [N][5] of this cycle (parity instrumentation; null in production)
 };
 
 // Layer 1 + LayerNorm + ReLU for the CTA's BT episodes with LS_MT threads (the 128-thread form of
@@ -624,6 +639,10 @@ ls_member_kernel(const __grid_constant__ CUtensorMap map_w2, const LsMemberParam
         if (t < n_env) {
             p.act[ep0 + t] = a;
             p.gap[ep0 + t] = gap;
+            if (p.logits) {
+#pragma unroll
+                for (int q = 0; q < NACT; ++q) p.logits[(ep0 + t) * NACT + q] = lg[q];
+            }
         }
     }
     __syncthreads();
@@ -661,6 +680,7 @@ struct LsOppParams {
     float* gap;
     const double* l1stats;
     int32_t* status;
+    float* logits;           // this cycle's [3][N][5] (parity instrumentation; null in production)
 };
 
 __device__ __forceinline__ void op_umma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
@@ -723,71 +743,20 @@ __device__ __forceinline__ void op_produce_chunk(const float* __restrict__ w1a, 
     }
 }
 
-// ---- CTA-pair (cta_group::2) plumbing ---------------------------------------------------------
-// In the PAIR form two CTAs on neighbouring SMs share one job of 256 episode rows: each produces the A
-// tile of its own 128 rows and holds HALF of the opponent matrix tile (128 of the 256 fc2 rows); one
-// tcgen05.mma.cta_group::2 (M = 256) issued by the leader drives both tensor cores, which exchange the B
-// halves over the pair link.  Per SM that is 8 KB of operand fetch per MMA instead of 12 KB and half the
-// TMA stream.  (Measured: no faster here, see launch_rollout_lockstep; kept as an opt-in.)  Barriers live at the same offsets
-// in both CTAs; "full" and "accumulator drained" are collected on the leader (remote arrives, TMA
-// complete_tx routed with the peer bit cleared), "empty" and "accumulator ready" are multicast commits.
-constexpr uint32_t CEV_PEER_MASK = 0xFEFFFFFFu;       // shared::cluster address of the same offset in the even CTA
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
-}
-// arrive on the barrier at this offset in the LEADER CTA (a plain local arrive when executed by the leader)
-__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(tc_smem_u32(bar) & CEV_PEER_MASK)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::
-            "r"(tc_smem_u32(dst)),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(tc_smem_u32(bar) & CEV_PEER_MASK), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
-    const uint16_t mask = 3;
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(
-                     tc_smem_u32(bar)),
-                 "h"(mask)
-                 : "memory");
-}
-constexpr uint32_t OP_IDESC_PAIR = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(256 >> 3) << 17) |
-                                   ((uint32_t)(256 >> 4) << 24);
-__device__ __forceinline__ void op_umma_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(OP_IDESC_PAIR), "r"(accumulate)
-        : "memory");
-}
-
-// stage geometry of the two forms
-template <bool PAIR>
-struct OpGeo {
-    static constexpr uint32_t B_BYTES = PAIR ? OP_B_BYTES / 2 : OP_B_BYTES;          // B hi (or lo) tile held by one CTA
-    static constexpr uint32_t STAGE_BYTES = 2 * OP_A_BYTES + 2 * B_BYTES;            // 96 KB / 64 KB
-    static constexpr int STAGES = PAIR ? 3 : 2;
-    static_assert((size_t)STAGES * STAGE_BYTES == OP_OFF_W1A, "both forms use the same 192 KB of stages");
-    static constexpr int ROWS_PER_JOB = PAIR ? 2 * OP_BM : OP_BM;
-    static constexpr uint32_t N_FULL = (PAIR ? 2 : 1) * (OP_PROD / 32) + 1;          // producer warps (of both CTAs) + TMA
-    static constexpr uint32_t N_TEMPTY = PAIR ? 8 : 4;
+// stage geometry: A hi | A lo | B hi | B lo
+struct Geo {
+    static constexpr uint32_t B_BYTES = OP_B_BYTES;
+    static constexpr uint32_t STAGE_BYTES = OP_STAGE_BYTES;
+    static constexpr int STAGES = OP_STAGES;
+    static constexpr int ROWS_PER_JOB = OP_BM;
+    static constexpr uint32_t N_FULL = OP_PROD / 32 + 1;          // producer warps + the TMA thread
+    static constexpr uint32_t N_TEMPTY = 4;
 };
 
-template <bool PAIR>
-__device__ __forceinline__ void ls_opp_body(const CUtensorMap& map_b, const LsOppParams& p) {
-    using Geo = OpGeo<PAIR>;
-    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
-    const int job0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-    const int job_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+__global__ void __launch_bounds__(OP_THREADS, 1)
+ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
+    const int job0 = (int)blockIdx.x;
+    const int job_stride = (int)gridDim.x;
     extern __shared__ unsigned char op_raw[];
     const uint32_t pad = (1024u - (smem_u32(op_raw) & 1023u)) & 1023u;
     if (pad > OP_SLACK) __trap();          // dynamic shared memory starts 1 KB aligned on sm_100; checked, not assumed
@@ -816,25 +785,15 @@ __device__ __forceinline__ void ls_opp_body(const CUtensorMap& map_b, const LsOp
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    if (PAIR) cluster_sync_all();          // both CTAs' barriers exist before anything can reach them
     if (warp == 13) {
-        if (PAIR) {
-            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
-                             tc_smem_u32(tmem_slot)),
-                         "r"(512u)
-                         : "memory");
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
-        } else {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
-                             tc_smem_u32(tmem_slot)),
-                         "r"(512u)
-                         : "memory");
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
-        }
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                         tc_smem_u32(tmem_slot)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
-    if (PAIR) cluster_sync_all();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     const int jobs_per_ok = p.n_tiles;
@@ -863,7 +822,7 @@ __device__ __forceinline__ void ls_opp_body(const CUtensorMap& map_b, const LsOp
                 asm volatile("bar.sync 2, 128;\n" ::: "memory");
                 cur_ok = okey;
             }
-            const int64_t j = (int64_t)tile * Geo::ROWS_PER_JOB + rank * OP_BM + q * 32 + lane;
+            const int64_t j = (int64_t)tile * Geo::ROWS_PER_JOB + q * 32 + lane;
             const bool valid = j < p.PE;
             const int64_t jj = valid ? j : p.PE - 1;
             const int64_t ep = ((jj / p.E) * p.K + k) * p.E + (jj % p.E);
@@ -935,10 +894,7 @@ __device__ __forceinline__ void ls_opp_body(const CUtensorMap& map_b, const LsOp
             }
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             __syncwarp();
-            if (lane == 0) {
-                if (PAIR) mbar_arrive_leader(bar_tempty + as);
-                else tc_mbar_arrive(bar_tempty + as);
-            }
+            if (lane == 0) tc_mbar_arrive(bar_tempty + as);
             bool fin = isfinite(mean) && isfinite(var);
 #pragma unroll
             for (int a = 0; a < NACT; ++a) {
@@ -951,6 +907,10 @@ __device__ __forceinline__ void ls_opp_body(const CUtensorMap& map_b, const LsOp
                 if (!fin) *flag = 1;
                 p.act[(int64_t)seat * p.N + ep] = a;
                 p.gap[(int64_t)seat * p.N + ep] = gap;
+                if (p.logits) {
+#pragma unroll
+                    for (int u = 0; u < NACT; ++u) p.logits[((int64_t)seat * p.N + ep) * NACT + u] = lg[u];
+                }
             }
         }
     } else if (warp < 12) {
@@ -977,7 +937,7 @@ __device__ __forceinline__ void ls_opp_body(const CUtensorMap& map_b, const LsOp
             float x[4][IN_GOOD];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int64_t jrow = (int64_t)tile * Geo::ROWS_PER_JOB + rank * OP_BM + lane + 32 * j;
+                const int64_t jrow = (int64_t)tile * Geo::ROWS_PER_JOB + lane + 32 * j;
                 const int64_t jj = jrow < p.PE ? jrow : p.PE - 1;
                 const int64_t ep = ((jj / p.E) * p.K + k) * p.E + (jj % p.E);
                 const float4* src = reinterpret_cast<const float4*>(p.obs + ((int64_t)seat * p.N + ep) * LS_OBS_PAD);
@@ -1041,10 +1001,7 @@ __device__ __forceinline__ void ls_opp_body(const CUtensorMap& map_b, const LsOp
 #endif
                 asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic writes -> tensor core reads
                 __syncwarp();
-                if (lane == 0) {                    // one arrival per producer warp
-                    if (PAIR) mbar_arrive_leader(bar_full + st);
-                    else tc_mbar_arrive(bar_full + st);
-                }
+                if (lane == 0) tc_mbar_arrive(bar_full + st);      // one arrival per producer warp
             }
         }
     } else if (warp == 12) {
@@ -1058,27 +1015,18 @@ __device__ __forceinline__ void ls_opp_body(const CUtensorMap& map_b, const LsOp
                     if (use > 0) tc_mbar_wait(bar_empty + st, (use - 1) & 1);
                     unsigned char* b_hi = stage_mem + (size_t)st * Geo::STAGE_BYTES + 2 * OP_A_BYTES;
 #if defined(CEV_EXP) && (CEV_EXP & 2)         // development experiment: bit 1 = no opponent matrix stream
-                    if (!PAIR || rank == 0) tc_mbar_arrive(bar_full + st);
+                    tc_mbar_arrive(bar_full + st);
                     (void)b_hi;
 #else
-                    if (PAIR) {
-                        // both CTAs load their half of B hi / B lo; the bytes complete on the LEADER's barrier,
-                        // which expects all four boxes
-                        if (rank == 0) tc_mbar_expect_tx(bar_full + st, 4 * Geo::B_BYTES);
-                        tma_load_2d_pair(b_hi, &map_b, bar_full + st, kt * OP_BK, (okey * 2 + 0) * H2 + (int)rank * (H2 / 2));
-                        tma_load_2d_pair(b_hi + Geo::B_BYTES, &map_b, bar_full + st, kt * OP_BK,
-                                         (okey * 2 + 1) * H2 + (int)rank * (H2 / 2));
-                    } else {
-                        tc_mbar_expect_tx(bar_full + st, 2 * OP_B_BYTES);
-                        tma_load_2d(b_hi, &map_b, bar_full + st, kt * OP_BK, (okey * 2 + 0) * H2);
-                        tma_load_2d(b_hi + OP_B_BYTES, &map_b, bar_full + st, kt * OP_BK, (okey * 2 + 1) * H2);
-                    }
+                    tc_mbar_expect_tx(bar_full + st, 2 * OP_B_BYTES);
+                    tma_load_2d(b_hi, &map_b, bar_full + st, kt * OP_BK, (okey * 2 + 0) * H2);
+                    tma_load_2d(b_hi + OP_B_BYTES, &map_b, bar_full + st, kt * OP_BK, (okey * 2 + 1) * H2);
 #endif
                 }
             }
         }
-    } else if (!PAIR || rank == 0) {
-        // ===================== MMA issuer (the leader CTA of a pair) =====================
+    } else {
+        // ===================== MMA issuer =====================
         uint32_t it = 0, pass = 0;
         for (int job = job0; job < p.n_jobs; job += job_stride, ++pass) {
             const uint32_t as = pass & 1, ause = pass >> 1;
@@ -1098,23 +1046,12 @@ __device__ __forceinline__ void ls_opp_body(const CUtensorMap& map_b, const LsOp
 #pragma unroll
                     for (int k8 = 0; k8 < OP_BK / 8; ++k8) {
                         const uint64_t ko = (uint64_t)(k8 * 2);           // 8 tf32 = 32 bytes
-                        if (PAIR) {
-                            op_umma_pair(d_tmem, a_lo + ko, b_hi + ko, (kt | k8) ? 1u : 0u);   // small terms first
-                            op_umma_pair(d_tmem, a_hi + ko, b_lo + ko, 1u);
-                            op_umma_pair(d_tmem, a_hi + ko, b_hi + ko, 1u);
-                        } else {
-                            op_umma(d_tmem, a_lo + ko, b_hi + ko, (kt | k8) ? 1u : 0u);
-                            op_umma(d_tmem, a_hi + ko, b_lo + ko, 1u);
-                            op_umma(d_tmem, a_hi + ko, b_hi + ko, 1u);
-                        }
+                        op_umma(d_tmem, a_lo + ko, b_hi + ko, (kt | k8) ? 1u : 0u);   // small terms first
+                        op_umma(d_tmem, a_hi + ko, b_lo + ko, 1u);
+                        op_umma(d_tmem, a_hi + ko, b_hi + ko, 1u);
                     }
-                    if (PAIR) {
-                        umma_commit_pair(bar_empty + st);
-                        if (kt == OP_KT - 1) umma_commit_pair(bar_tfull + as);
-                    } else {
-                        umma_commit(bar_empty + st);
-                        if (kt == OP_KT - 1) umma_commit(bar_tfull + as);
-                    }
+                    umma_commit(bar_empty + st);
+                    if (kt == OP_KT - 1) umma_commit(bar_tfull + as);
                 }
                 __syncwarp();
             }
@@ -1122,26 +1059,9 @@ __device__ __forceinline__ void ls_opp_body(const CUtensorMap& map_b, const LsOp
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
-    if (PAIR) cluster_sync_all();          // the peer's tensor core may still read this CTA's shared memory / TMEM
     if (threadIdx.x == 0 && *flag && p.status) atomicOr(p.status, CEV_STATUS_NONFINITE);
-    if (warp == 13) {
-        if (PAIR) {
-            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u) : "memory");
-        } else {
-            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u) : "memory");
-        }
-    }
-}
-
-__global__ void __launch_bounds__(OP_THREADS, 1)
-ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
-    ls_opp_body<false>(map_b, p);
-}
-
-// CTA-pair form: clusters of two CTAs, tcgen05 cta_group::2 (M = 256 per MMA)
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(OP_THREADS, 1)
-ls_opp_pair_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
-    ls_opp_body<true>(map_b, p);
+    if (warp == 13)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
 
@@ -1177,7 +1097,6 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
                                       (int)LsMemberSmem::total));
         CEV_CUDA(cudaFuncSetAttribute(ls_member_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CEV_CUDA(cudaFuncSetAttribute(ls_opp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OP_SMEM));
-        CEV_CUDA(cudaFuncSetAttribute(ls_opp_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OP_SMEM));
         configured[h->device] = true;
     }
 
@@ -1259,12 +1178,7 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
     op.K = p.K;
     op.E = p.E;
     op.PE = (int64_t)p.P * p.E;
-    // CEV_LS_PAIR=1 selects the CTA-pair (cta_group::2) form of the opponent kernel.  It is parity-green but
-    // 8-10 % slower than the single-CTA form on this workload: the MMA chain alone already runs at the
-    // MEASURED dense TF32 rate (half of MEASURED_PEAKS.json's bf16 figure) in both forms, so sharing the B
-    // operand buys nothing and the cross-CTA barrier traffic costs a little.
-    static const int use_pair = getenv("CEV_LS_PAIR") ? atoi(getenv("CEV_LS_PAIR")) : 0;
-    const int rows_per_job = use_pair ? 2 * OP_BM : OP_BM;
+    const int rows_per_job = OP_BM;
     op.n_tiles = (int)((op.PE + rows_per_job - 1) / rows_per_job);
     op.n_jobs = 2 * p.K * op.n_tiles;
     op.N = N;
@@ -1274,26 +1188,19 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
     op.l1stats = b.l1stats;
     op.status = p.status;
     int opp_grid = op.n_jobs < h->n_sm ? op.n_jobs : h->n_sm;
-    if (use_pair) {
-        const int pairs = h->n_sm / 2;
-        opp_grid = 2 * (op.n_jobs < pairs ? op.n_jobs : pairs);
-        // the pair form loads [128 x 32] boxes: one half of B per CTA
-        cuuint64_t dims[2] = {(cuuint64_t)H1, (cuuint64_t)2 * p.K * 2 * H2};
-        cuuint64_t strides[1] = {(cuuint64_t)H1 * 4};
-        cuuint32_t box[2] = {OP_BK, OP_BN / 2};
-        cuuint32_t estr[2] = {1, 1};
-        CUresult r = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, b.w2split, dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) {
-            set_error("rollout_lockstep: cuTensorMapEncodeTiled(opponent fc2, pair form) failed with %d", (int)r);
-            return CEV_ERR_CUDA;
-        }
-    }
 
     // development aids: CEV_LS_SKIP bit 0 = no opponent kernel, bit 1 = no member kernel (timing only,
     // results are then invalid); CEV_LS_FORK=1 = opponent kernel on a side stream beside the member kernel
     static const int skip = getenv("CEV_LS_SKIP") ? atoi(getenv("CEV_LS_SKIP")) : 0;
+    // CEV_LS_MEMBER_PAD = extra dynamic shared memory (bytes) per member CTA: 16384 leaves room for ONE member CTA
+    // per SM (timing experiment: what a member CTA delivers when it does not share the SM with a second one)
+    static const int member_pad = getenv("CEV_LS_MEMBER_PAD") ? atoi(getenv("CEV_LS_MEMBER_PAD")) : 0;
+    static bool pad_configured = false;
+    if (member_pad > 0 && !pad_configured) {
+        CEV_CUDA(cudaFuncSetAttribute(ls_member_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)LsMemberSmem::total + member_pad));
+        pad_configured = true;
+    }
     static const int want_fork = getenv("CEV_LS_FORK") ? atoi(getenv("CEV_LS_FORK")) : 0;
     // The two forwards of a world step are independent (same observations), use different pipes
     // (tensor vs FP32/HBM) and both end in a partial wave, so running them on two streams lets the
@@ -1308,6 +1215,12 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
     ep.last = p.n_cycles == 0;
     ls_init_kernel<<<env_blocks, 256, 0, stream>>>(ep);
     for (int c = 0; c < p.n_cycles; ++c) {
+        if (p.trace_logits) {
+            op.logits = p.trace_logits + (size_t)c * 3 * N * NACT;
+            mp.logits = op.logits + (size_t)ms * N * NACT;
+        }
+        ep.forced = p.trace_forced ? p.trace_forced + (size_t)c * 3 * N : nullptr;
+        ep.act_out = p.trace_actions ? p.trace_actions + (size_t)c * 3 * N : nullptr;
         // optional per-kernel CUDA-event timing on the launch stream (cev_kernel_timing_enable)
         auto tick = [&](int which, int end) {
             if (h->timing_on && h->timing_n[which] < CEV_TIMING_MAX) {
@@ -1319,19 +1232,17 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
             if (fork) {
                 CEV_CUDA(cudaEventRecord(h->fork_ev, stream));
                 CEV_CUDA(cudaStreamWaitEvent(h->side_stream, h->fork_ev, 0));
-                if (use_pair) ls_opp_pair_kernel<<<opp_grid, OP_THREADS, OP_SMEM, h->side_stream>>>(map_b, op);
-                else ls_opp_kernel<<<opp_grid, OP_THREADS, OP_SMEM, h->side_stream>>>(map_b, op);
+                ls_opp_kernel<<<opp_grid, OP_THREADS, OP_SMEM, h->side_stream>>>(map_b, op);
                 CEV_CUDA(cudaEventRecord(h->join_ev, h->side_stream));
             } else {
                 tick(1, 0);
-                if (use_pair) ls_opp_pair_kernel<<<opp_grid, OP_THREADS, OP_SMEM, stream>>>(map_b, op);
-                else ls_opp_kernel<<<opp_grid, OP_THREADS, OP_SMEM, stream>>>(map_b, op);
+                ls_opp_kernel<<<opp_grid, OP_THREADS, OP_SMEM, stream>>>(map_b, op);
                 tick(1, 1);
             }
         }
         if (!(skip & 2)) {
             tick(0, 0);
-            ls_member_kernel<<<(unsigned)member_ctas, LS_MT, LsMemberSmem::total, stream>>>(map_w2, mp);
+            ls_member_kernel<<<(unsigned)member_ctas, LS_MT, LsMemberSmem::total + member_pad, stream>>>(map_w2, mp);
             tick(0, 1);
         }
         if (fork && !(skip & 1)) CEV_CUDA(cudaStreamWaitEvent(stream, h->join_ev, 0));

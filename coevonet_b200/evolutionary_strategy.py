@@ -15,7 +15,7 @@ import torch
 from tqdm import tqdm
 
 from . import engine as _engine
-from . import layout, ops
+from . import layout
 from .utils.game_logic_functions import create_agent, play_game
 from .utils.utils_pth_and_plots import plot_experiment_metrics, plot_weights_logging, save_model
 
@@ -58,13 +58,16 @@ def mutate_weights(env, agent_0, agent_1, adversary, args, role, step, weights_l
 
 def compute_weight_update(noises, rewards, args, role, individual_weights=None, population_weights=None):
     """delta = lr / (n * sigma) * noises^T fitness (evolutionary_strategy.py:120-148) for
-    caller-supplied noise arrays.  The contraction is a [D x P] GEMV over host
-    data handed in by the caller; it runs on the device (torch matmul is library
-    plumbing here -- the population path uses the K6 kernel, which regenerates
-    the noise instead of reading it)."""
+    caller-supplied noise arrays: the K6 kernel in its members form with theta = 0, so the
+    ``noises`` rows themselves are the sigma*z terms (any row length: layout-agnostic path)."""
+    from . import ops
     from .utils.game_logic_functions import _device, diversity_penalty
     dev = _device()
-    noises = torch.from_numpy(np.asarray(noises, dtype=np.float32)).to(dev)
+    noises = np.ascontiguousarray(np.asarray(noises, dtype=np.float32))
+    n, D = noises.shape
+    pitch = (D + 31) // 32 * 32
+    rows = torch.zeros((n, pitch), dtype=torch.float32, device=dev)
+    rows[:, :D] = torch.from_numpy(noises).to(dev)
     fit = torch.from_numpy(np.asarray(rewards, dtype=np.float32)).to(dev)
     diversity = None
     if args.fitness_sharing:
@@ -73,8 +76,15 @@ def compute_weight_update(noises, rewards, args, role, individual_weights=None, 
         fit = fit / (1 + diversity)
     sigma = {"agent_0": args.mutation_power_agent_0, "agent_1": args.mutation_power_agent_1,
              "adversary_0": args.mutation_power_adversary}[role]
-    upd = (args.learning_rate / (noises.shape[0] * sigma)) * (noises.T @ fit)
-    return upd.cpu().numpy().astype(np.float32), diversity
+    zero = torch.zeros(pitch, dtype=torch.float32, device=dev)
+    upd = ops.es_update_members(fit.to(torch.float64).contiguous(), rows, zero, 0, sigma, args.learning_rate, n)
+    return upd[:D].cpu().numpy().astype(np.float32), diversity
+
+
+def checkpoint_path(output_dir):
+    """Engine checkpoint written beside the reference-format ``.pth`` files (true resume, N2)."""
+    rank = _engine.Comm().rank
+    return os.path.join(output_dir, f"engine_state_rank{rank}.pt")
 
 
 def evolution_strategy_train(env, args, output_dir):
@@ -89,63 +99,72 @@ def evolution_strategy_train(env, args, output_dir):
     from .utils.game_logic_functions import _device
     dev = _device()
     comm = _engine.Comm()
+    # every rank builds the base agents from rank 0's generator state (unseeded runs included)
+    _engine.sync_torch_rng(comm, dev)
     agents = {r: create_agent(env, args, role=r) for r in ROLES}
-    for name, r in (("agent_0", "agent_0"), ("agent_1", "agent_1"), ("adversary", "adversary_0")):
-        print(f"\nNumber of parameters for {name} network: {sum(p.numel() for p in agents[r].model.parameters())}")
+    if comm.rank == 0:
+        for name, r in (("agent_0", "agent_0"), ("agent_1", "agent_1"), ("adversary", "adversary_0")):
+            print(f"\nNumber of parameters for {name} network: "
+                  f"{sum(p.numel() for p in agents[r].model.parameters())}")
     theta = {r: agents[r].model.flat_row() for r in ROLES}
     eng = _engine.ESEngine(args, dev, theta, env=env, comm=comm)
+    start = 0
+    if getattr(args, "resume", False) and os.path.isfile(checkpoint_path(output_dir)):
+        eng.load_state_dict(torch.load(checkpoint_path(output_dir), weights_only=False))
+        start = eng.gen
+        if comm.rank == 0:
+            print(f"Resuming from generation {start} ({checkpoint_path(output_dir)})")
 
-    rewards = {r: [] for r in ROLES}
     wlog = {r: [] for r in ROLES}
     diversity = {r: [] if args.fitness_sharing else None for r in ROLES}
     fitness = {r: [] if args.fitness_sharing else None for r in ROLES}
-    sigma_hist = {r: [eng.sigma(r)] if args.adaptive else None for r in ROLES}
-    best = {r: -float("inf") for r in ROLES}
-    stale = {r: 0 for r in ROLES}
+    # the per-generation host view (rewards, sigma history) is read back only when something on the host
+    # consumes it: plots, checkpoints, early stopping, the last generation
+    want_plots = comm.rank == 0 and getattr(args, "plots", True)
+    pidx = {r: torch.from_numpy(layout.fc_perturbable_index(layout.OBS_DIM[r])).to(dev) for r in ROLES}
 
-    for gen in tqdm(range(args.generations), desc="Training Generations"):
-        ev = dict(zip(ROLES, eng.step()))
-        for r in ROLES:
-            rewards[r].append(ev[r])
-            if args.fitness_sharing:
-                diversity[r].append(eng.diversity[r])
-                fitness[r].append(ev[r] / (1 + eng.diversity[r]))
+    for gen in tqdm(range(start, args.generations), desc="Training Generations", initial=start,
+                    total=args.generations):
+        eng.step(sync=False)
+        last = gen == args.generations - 1
         if getattr(args, "log_weight_stats", True):
-            # per-generation statistics of the base weights (the reference logs them per member,
-            # MPE/mpe_agent.py:30-50; one sample per generation keeps the plot and drops P syncs)
+            # statistics of the base weights, kept on the device until plotted (the reference logs them per
+            # perturbed member, MPE/mpe_agent.py:30-50: args.log_member_weight_stats restores that, K5 + one
+            # reduction kernel per role, in eng.weight_stats)
             for r in ROLES:
-                pidx = torch.from_numpy(layout.fc_perturbable_index(layout.OBS_DIM[r])).to(dev)
-                w = eng.theta[r][pidx]
-                wlog[r].append({"step": gen, "mean": float(w.mean()), "min": float(w.min()),
-                                "max": float(w.max()), "std": float(w.std())})
-        if args.adaptive:
-            _engine.adapt_sigma(args, rewards["agent_0"], rewards["agent_1"], rewards["adversary_0"], gen)
+                w = eng.theta[r][pidx[r]]
+                wlog[r].append((gen, torch.stack([w.mean(), w.min(), w.max(), w.std()])))
+        if args.fitness_sharing:
             for r in ROLES:
-                sigma_hist[r].append(eng.sigma(r))
-        if args.early_stopping:
-            stop = None
-            for r in ROLES:
-                if ev[r] > best[r] + args.min_delta:
-                    best[r], stale[r] = ev[r], 0
-                else:
-                    stale[r] += 1
-            for r, name in (("agent_0", "agent_0"), ("agent_1", "agent_1"), ("adversary_0", "adversary")):
-                if stale[r] >= args.patience:
-                    print(f"Early stopping triggered at generation {gen} for {name}. Best reward: {best[r]}")
-                    stop = r
-                    break
-            if stop is not None:
-                break
-        if (args.save or gen == args.generations - 1) and comm.rank == 0:
+                diversity[r].append(eng.diversity[r])
+        stop = eng.should_stop() if args.early_stopping else 0
+        if stop:
+            hs = eng.host_state()
+            name = {"agent_0": "agent_0", "agent_1": "agent_1", "adversary_0": "adversary"}[ROLES[stop - 1]]
+            print(f"Early stopping triggered at generation {gen} for {name}. "
+                  f"Best reward: {hs['best'][ROLES[stop - 1]]}")
+            break
+        if (args.save or last) and comm.rank == 0:
             for r in ROLES:
                 agents[r].model.load_flat_row(eng.theta[r])
                 if args.save:
                     save_model(agents[r], files[r])
-        if comm.rank == 0 and getattr(args, "plots", True):
+        if args.save:
+            torch.save(eng.state_dict(), checkpoint_path(output_dir))
+        if want_plots:
+            hs = eng.host_state()
+            div_host = {r: [float(d) for d in diversity[r]] if args.fitness_sharing else None for r in ROLES}
             for r in ROLES:
-                plot_experiment_metrics(rewards=rewards[r], mutation_power_history=sigma_hist[r],
-                                        fitness=fitness[r], diversity=diversity[r], file_path=plots[r], args=args)
-            plot_weights_logging(weights_plot, wlog["agent_0"], wlog["agent_1"], wlog["adversary_0"])
+                rew = list(hs["rewards"][r])
+                fit = [x / (1 + d) for x, d in zip(rew[start:], div_host[r])] if args.fitness_sharing else None
+                plot_experiment_metrics(rewards=rew,
+                                        mutation_power_history=list(hs["sigma_history"][r]) if args.adaptive else None,
+                                        fitness=fit, diversity=div_host[r], file_path=plots[r], args=args)
+            logs = {r: [{"step": g, "mean": float(t[0]), "min": float(t[1]), "max": float(t[2]), "std": float(t[3])}
+                        for g, t in wlog[r]] for r in ROLES}
+            plot_weights_logging(weights_plot, logs["agent_0"], logs["agent_1"], logs["adversary_0"])
+    eng.check_status()
+    eng.write_back_args()                 # the reference leaves the adapted sigmas in `args`
     for r in ROLES:
         agents[r].model.load_flat_row(eng.theta[r])
     args._es_engine = eng

@@ -105,44 +105,56 @@ def genetic_algorithm_train(env, agent, args, output_dir):
         hof_rows = {r: ops.fc_init(layout.OBS_DIM[r], seed, r, P, H, dev) for r in ROLES}
         # Appendix C #3: diversity is measured against the LAST founder created for each role
         founder = {r: ops.fc_init(layout.OBS_DIM[r], seed, r, P - 1, 1, dev)[0] for r in ROLES}
-        for name, role in (("agent_0", "agent_1"), ("agent_1", "agent_0"), ("adversary", "adversary_0")):
-            print(f"\nNumber of parameters for {name} network: {layout.fc_dim(layout.OBS_DIM[role])}")
+        if comm.rank == 0:
+            for name, role in (("agent_0", "agent_1"), ("agent_1", "agent_0"), ("adversary", "adversary_0")):
+                print(f"\nNumber of parameters for {name} network: {layout.fc_dim(layout.OBS_DIM[role])}")
     else:
+        # every rank draws the founders from rank 0's generator state (unseeded runs included), so the
+        # shards are the row blocks of ONE population and the replicated rows agree
+        _engine.sync_torch_rng(comm, dev)
         hof_agents, pop_agents = build_initial_state(env, args)
-        for name, role in (("agent_0", "agent_1"), ("agent_1", "agent_0"), ("adversary", "adversary_0")):
-            n_par = sum(p.numel() for p in hof_agents[role][0].model.parameters())
-            print(f"\nNumber of parameters for {name} network: {n_par}")
+        if comm.rank == 0:
+            for name, role in (("agent_0", "agent_1"), ("agent_1", "agent_0"), ("adversary", "adversary_0")):
+                n_par = sum(p.numel() for p in hof_agents[role][0].model.parameters())
+                print(f"\nNumber of parameters for {name} network: {n_par}")
         pop_rows = {r: layout.pack_models([a.model for a in pop_agents[r][sl]], layout.OBS_DIM[r]) for r in ROLES}
         hof_rows = {r: layout.pack_models([a.model for a in hof_agents[r]], layout.OBS_DIM[r]) for r in ROLES}
         # Appendix C #3: diversity is measured against the LAST founder created for each role
         founder = {r: layout.pack_models([pop_agents[r][-1].model], layout.OBS_DIM[r])[0] for r in ROLES}
         del pop_agents
     eng = _engine.GAEngine(args, dev, pop_rows, hof_rows, founder, env=env, comm=comm)
+    ckpt = os.path.join(output_dir, f"engine_state_rank{comm.rank}.pt")
+    start = 0
+    if getattr(args, "resume", False) and os.path.isfile(ckpt):
+        eng.load_state_dict(torch.load(ckpt, weights_only=False))
+        start = eng.gen
+        if comm.rank == 0:
+            print(f"Resuming from generation {start} ({ckpt})")
 
-    rewards = {r: [] for r in ROLES}
     diversity = {r: [] if args.fitness_sharing else None for r in ROLES}
-    fitness = {r: [] if args.fitness_sharing else None for r in ROLES}
-    sigma_hist = {r: [eng.sigma(r)] if args.adaptive else None for r in ROLES}
+    want_plots = comm.rank == 0 and getattr(args, "plots", True)
 
-    for gen in tqdm(range(args.generations), desc="Generations"):
-        ev = eng.step()
-        ev = dict(zip(ROLES, ev))
+    for gen in tqdm(range(start, args.generations), desc="Generations", initial=start, total=args.generations):
+        eng.step(sync=False)
         if args.save and comm.rank == 0:
             for r in ROLES:
                 save_model(_rows_to_agents(eng.hof[r], env, args, r), files[r][0])
                 save_model(_rows_to_agents(eng.elites[r], env, args, r), files[r][1])
-        for r in ROLES:
-            rewards[r].append(ev[r])
-            if args.fitness_sharing:
+        if args.save:
+            torch.save(eng.state_dict(), ckpt)
+        if args.fitness_sharing:
+            for r in ROLES:
                 diversity[r].append(eng.diversity[r])
-                fitness[r].append(ev[r] / (1 + eng.diversity[r]))
-        if args.adaptive:
-            _engine.adapt_sigma(args, rewards["agent_0"], rewards["agent_1"], rewards["adversary_0"], gen)
+        if want_plots:
+            hs = eng.host_state()
             for r in ROLES:
-                sigma_hist[r].append(eng.sigma(r))
-        if comm.rank == 0 and getattr(args, "plots", True):
-            for r in ROLES:
-                plot_experiment_metrics(rewards=rewards[r], mutation_power_history=sigma_hist[r],
-                                        fitness=fitness[r], diversity=diversity[r], file_path=plots[r], args=args)
+                rew = list(hs["rewards"][r])
+                div = [float(d) for d in diversity[r]] if args.fitness_sharing else None
+                fit = [x / (1 + d) for x, d in zip(rew[start:], div)] if args.fitness_sharing else None
+                plot_experiment_metrics(rewards=rew,
+                                        mutation_power_history=list(hs["sigma_history"][r]) if args.adaptive else None,
+                                        fitness=fit, diversity=div, file_path=plots[r], args=args)
+    eng.check_status()
+    eng.write_back_args()          # the reference leaves the adapted sigmas in `args`
     args._ga_engine = eng          # handle for callers that want the final device state
     return None

@@ -71,6 +71,13 @@ def parse_arguments(argv=None):
     p.add_argument("--seed", type=int, default=1870300, help="run seed of the Philox noise streams")
     p.add_argument("--torch_seed", type=int, default=None, help="torch.manual_seed for the founders")
     p.add_argument("--no_plots", action="store_true")
+    p.add_argument("--resume", action="store_true",
+                   help="continue from <output_dir>/engine_state_rank<r>.pt (written next to the reference-format "
+                        ".pth files when --save is set): populations / base rows, HoF ring, sigmas, reward history, "
+                        "generation counter, Philox seed, host init-state stream")
+    p.add_argument("--log_member_weight_stats", action="store_true",
+                   help="ES: per-MEMBER statistics of the perturbed weights every generation (the reference's "
+                        "log_weight_statistics, MPE/mpe_agent.py:30-50), reduced on the device")
     return p.parse_args(argv)
 
 
@@ -125,6 +132,8 @@ class Args:
         self.play_discarded_hof_games = a.play_discarded_hof_games
         self.update_from_members = not a.regenerate_noise
         self.plots = not a.no_plots
+        self.resume = a.resume
+        self.log_member_weight_stats = a.log_member_weight_stats
 
     def print_attributes(self, args=None):
         for k, v in vars(self).items():

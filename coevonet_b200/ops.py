@@ -144,6 +144,8 @@ def mpe_rollout(member_role, members, opp_a, opp_b, init, *, n_cycles=MAX_CYCLES
         raise _lib.CevError("members must be float32 and init float64")
     if out is None:
         out = torch.empty((P, K, E, _lib.ROLLOUT_OUT_DIM), dtype=torch.float64, device=dev)
+    if P == 0:
+        return out                        # an empty shard plays nothing
     cfg = RolloutCfg(int(n_cycles), int(bool(pos_first)), int(variant), 0)
     _, n_launch = rollout_plan(dev.index, P, K, E, n_cycles, variant)
     check(_call("cev_mpe_rollout_f32",
@@ -152,6 +154,32 @@ def mpe_rollout(member_role, members, opp_a, opp_b, init, *, n_cycles=MAX_CYCLES
         _ptr(init), int(bool(init_shared)), E, ctypes.byref(cfg), _ptr(out), _ptr(status),
         _stream(dev), launches=n_launch), "cev_mpe_rollout_f32")
     return out
+
+
+def mpe_rollout_trace(member_role, members, opp_a, opp_b, init, *, n_cycles=MAX_CYCLES, pos_first=True,
+                      forced_actions=None, status=None):
+    """K1 lockstep kernels with parity instrumentation: returns (out fp64 [P,K,E,4], logits fp32
+    [n_cycles,3,N,5], actions int32 [n_cycles,3,N]); ``forced_actions`` int32 [n_cycles,3,N] replays
+    a given action trace (teacher forcing).  Seats in world order, N = P*K*E."""
+    dev = _need_cuda(members, opp_a, opp_b, init, forced_actions, status)
+    seat = layout.SEAT_OF[member_role] if isinstance(member_role, str) else int(member_role)
+    P, K = members.shape[0], opp_a.shape[0]
+    if init.dim() != 4 or init.shape[:2] != (P, K) or init.shape[3] != _lib.INIT_STATE_DIM:
+        raise _lib.CevError("init must be fp64 [P, K, E, 11]")
+    E = init.shape[2]
+    N = P * K * E
+    if forced_actions is not None and (forced_actions.dtype != torch.int32 or
+                                       tuple(forced_actions.shape) != (n_cycles, 3, N)):
+        raise _lib.CevError("forced_actions must be int32 [n_cycles, 3, N]")
+    out = torch.empty((P, K, E, _lib.ROLLOUT_OUT_DIM), dtype=torch.float64, device=dev)
+    logits = torch.zeros((n_cycles, 3, N, layout.NACT), dtype=torch.float32, device=dev)
+    actions = torch.zeros((n_cycles, 3, N), dtype=torch.int32, device=dev)
+    cfg = RolloutCfg(int(n_cycles), int(bool(pos_first)), 3, 0)
+    check(_call("cev_mpe_rollout_trace_f32", _h(dev), seat, _ptr(members), P, members.stride(0),
+                _ptr(opp_a), opp_a.stride(0), _ptr(opp_b), opp_b.stride(0), K, _ptr(init), 0, E,
+                ctypes.byref(cfg), _ptr(forced_actions), _ptr(logits), _ptr(actions), _ptr(out), _ptr(status),
+                _stream(dev), launches=3 + 3 * int(n_cycles)), "cev_mpe_rollout_trace_f32")
+    return out, logits, actions
 
 
 def mpe_rollout_indexed(w_adv, w_a0, w_a1, idx, init, *, n_cycles=MAX_CYCLES, pos_first=True,
@@ -188,38 +216,55 @@ def fc_forward(rows, in_dim, obs, idx=None, *, status=None):
     return logits, actions
 
 
+def _sigma_args(sigma):
+    """(by-value float, device pointer) of a mutation power given as a Python float or as a
+    one-element fp64 DEVICE tensor (a slot of the generation state, read by the kernel)."""
+    if torch.is_tensor(sigma):
+        if sigma.dtype != torch.float64 or sigma.numel() != 1 or not sigma.is_cuda:
+            raise _lib.CevError("a device sigma must be a one-element float64 CUDA tensor")
+        return 0.0, _ptr(sigma)
+    return float(sigma), ctypes.c_void_p(0)
+
+
 def ga_repopulate(elites, dim, sigma, seed, role, gen, row0, n_rows, *, out=None, noise_out=None):
     """K3: rows [row0, row0+n_rows) of the next GA population."""
     dev = _need_cuda(elites, out, noise_out)
+    sig, sig_dev = _sigma_args(sigma)
     pitch = elites.stride(0)
     if out is None:
         out = torch.empty((n_rows, pitch), dtype=torch.float32, device=dev)
     role_id = layout.ROLE_ID[role] if isinstance(role, str) else int(role)
     check(_call("cev_ga_repopulate_f32", 
-        _h(dev), _ptr(elites), elites.shape[0], int(dim), pitch, float(sigma),
+        _h(dev), _ptr(elites), elites.shape[0], int(dim), pitch, sig, sig_dev,
         int(seed), role_id, int(gen), int(row0), int(n_rows), _ptr(out), _ptr(noise_out),
         _stream(dev)), "cev_ga_repopulate_f32")
     return out
 
 
-def gather_rows(src, idx, *, out=None):
-    dev = _need_cuda(src, idx, out)
+def gather_rows(src, idx, *, row0=0, n_local=None, out=None):
+    """dst[i] = src[idx[i] - row0]; with ``n_local`` the ids are GLOBAL and rows outside this rank's
+    block [row0, row0+n_local) come back as zeros (summed over ranks = the elite broadcast)."""
+    dev = _need_cuda(idx, out, src if src.numel() else None)
     if idx.dtype != torch.int64:
         raise _lib.CevError("gather_rows: idx must be int64")
+    pitch = src.stride(0) if src.dim() == 2 and src.shape[0] > 0 else src.shape[-1]
     if out is None:
-        out = torch.empty((idx.shape[0], src.stride(0)), dtype=torch.float32, device=dev)
-    check(_call("cev_gather_rows_f32", _h(dev), _ptr(src), src.stride(0), _ptr(idx),
-                                     idx.shape[0], _ptr(out), _stream(dev)), "cev_gather_rows_f32")
+        out = torch.empty((idx.shape[0], pitch), dtype=torch.float32, device=dev)
+    check(_call("cev_gather_rows_f32", _h(dev), _ptr(src) if src.numel() else ctypes.c_void_p(0), pitch, _ptr(idx),
+                idx.shape[0], int(row0), -1 if n_local is None else int(n_local), _ptr(out), _stream(dev)),
+          "cev_gather_rows_f32")
     return out
 
 
-def select_topk(fitness, k):
-    """K4: int64[k] indices of the k largest fitness values (desc, ties -> lower index)."""
+def select_topk(fitness, k, order=_lib.ORDER_STABLE_DESC):
+    """K4: int64[k] indices of the k largest fitness values, descending.  ``order`` 0: ties -> lower
+    index, NaN last; 1 (``ORDER_REFERENCE``): the reference's ``np.argsort(f)[::-1]`` with a stable
+    sort: ties -> higher index, NaN first."""
     dev = _need_cuda(fitness)
     if fitness.dtype != torch.float64 or fitness.dim() != 1:
         raise _lib.CevError("select_topk: fitness must be float64 [P]")
     idx = torch.empty(k, dtype=torch.int64, device=dev)
-    check(_call("cev_select_topk_f64", _h(dev), _ptr(fitness), fitness.shape[0], int(k),
+    check(_call("cev_select_topk_f64", _h(dev), _ptr(fitness), fitness.shape[0], int(k), int(order),
                                      _ptr(idx), _stream(dev)), "cev_select_topk_f64")
     return idx
 
@@ -233,8 +278,9 @@ def es_perturb(theta, in_dim, sigma, seed, role, gen, row0, n_rows, *, out=None,
     if out is None:
         out = torch.empty((n_rows, pitch), dtype=torch.float32, device=dev)
     role_id = layout.ROLE_ID[role] if isinstance(role, str) else int(role)
+    sig, sig_dev = _sigma_args(sigma)
     check(_call("cev_es_perturb_f32", 
-        _h(dev), _ptr(theta), int(in_dim), float(sigma), int(seed), role_id, int(gen),
+        _h(dev), _ptr(theta), int(in_dim), sig, sig_dev, int(seed), role_id, int(gen),
         int(row0), int(n_rows), pitch, _ptr(out), _ptr(noise_out), _stream(dev)), "cev_es_perturb_f32")
     return out
 
@@ -250,7 +296,8 @@ def es_perturb_dqn(theta, c_in, n_actions, sigma, seed, role, gen, row0, n_rows,
     if out is None:
         out = torch.empty((n_rows, pitch), dtype=torch.float32, device=dev)
     role_id = layout.ROLE_ID[role] if isinstance(role, str) else int(role)
-    check(_call("cev_es_perturb_prefix_f32", _h(dev), _ptr(theta), d_pert, total, float(sigma), int(seed), role_id,
+    sig, sig_dev = _sigma_args(sigma)
+    check(_call("cev_es_perturb_prefix_f32", _h(dev), _ptr(theta), d_pert, total, sig, sig_dev, int(seed), role_id,
                 int(gen), int(row0), int(n_rows), pitch, _ptr(out), _stream(dev)), "cev_es_perturb_prefix_f32")
     return out
 
@@ -265,8 +312,9 @@ def es_update(fitness, in_dim, sigma, lr, n_total, seed, role, gen, row0, *, out
     if out is None:
         out = torch.empty(pitch, dtype=torch.float32, device=dev)
     role_id = layout.ROLE_ID[role] if isinstance(role, str) else int(role)
+    sig, sig_dev = _sigma_args(sigma)
     check(_call("cev_es_update_f32", 
-        _h(dev), _ptr(fitness), int(in_dim), float(sigma), float(lr), int(n_total),
+        _h(dev), _ptr(fitness), int(in_dim), sig, sig_dev, float(lr), int(n_total),
         int(seed), role_id, int(gen), int(row0), fitness.shape[0], _ptr(out), _stream(dev)),
         "cev_es_update_f32")
     return out
@@ -275,18 +323,64 @@ def es_update(fitness, in_dim, sigma, lr, n_total, seed, role, gen, row0, *, out
 def es_update_members(fitness, members, theta, in_dim, sigma, lr, n_total, *, out=None):
     """K6 from the materialised members: delta fp32[pitch] = lr/(n_total*sigma) * sum_i (members[i] - theta)
     * fitness_i (the reference's `noises` array read back instead of regenerated)."""
-    dev = _need_cuda(fitness, members, theta, out)
+    dev = _need_cuda(theta, out, fitness if fitness.numel() else None, members if members.numel() else None)
     if fitness.dtype != torch.float64 or fitness.shape[0] != members.shape[0]:
         raise _lib.CevError("es_update_members: fitness must be float64 [n_rows]")
     pitch = layout.fc_pitch(in_dim) if in_dim else members.stride(0)      # in_dim 0: any row layout (DeepQN)
-    if members.stride(0) != pitch or theta.numel() < pitch:
+    if (members.shape[0] > 0 and members.stride(0) != pitch) or theta.numel() < pitch:
         raise _lib.CevError("es_update_members: members / theta must use the padded row pitch")
     if out is None:
         out = torch.empty(pitch, dtype=torch.float32, device=dev)
-    check(_call("cev_es_update_members_f32", _h(dev), _ptr(fitness), _ptr(members), pitch, _ptr(theta),
-                int(in_dim), float(sigma), float(lr), int(n_total), members.shape[0], _ptr(out), _stream(dev)),
+    sig, sig_dev = _sigma_args(sigma)
+    empty = members.shape[0] == 0
+    check(_call("cev_es_update_members_f32", _h(dev), ctypes.c_void_p(0) if empty else _ptr(fitness),
+                ctypes.c_void_p(0) if empty else _ptr(members), pitch, _ptr(theta),
+                int(in_dim), sig, sig_dev, float(lr), int(n_total), members.shape[0], _ptr(out), _stream(dev)),
           "cev_es_update_members_f32")
     return out
+
+
+def weight_stats(rows, in_dim, *, out=None):
+    """fp32 [n_rows, 4] = (mean, min, max, population std) of every row's perturbable weights
+    (``MPEAgent.log_weight_statistics``, ``MPE/mpe_agent.py:30-50``)."""
+    n = rows.shape[0]
+    if out is None:
+        out = torch.empty((n, 4), dtype=torch.float32, device=rows.device)
+    if n == 0:
+        return out
+    dev = _need_cuda(rows, out)
+    check(_call("cev_weight_stats_f32", _h(dev), _ptr(rows), n, rows.stride(0), int(in_dim), _ptr(out),
+                _stream(dev)), "cev_weight_stats_f32")
+    return out
+
+
+def generation_state(sigmas, hist_capacity, device):
+    """A fresh device generation state (fp64; ``CEV_GS_*`` slots): generation 0, the three mutation
+    powers (agent_0, agent_1, adversary_0), best = -inf, empty histories."""
+    n = int(load().cev_generation_state_doubles(int(hist_capacity)))
+    gs = torch.zeros(n, dtype=torch.float64)
+    gs[_lib.GS_SIGMA:_lib.GS_SIGMA + 3] = torch.tensor([float(x) for x in sigmas], dtype=torch.float64)
+    gs[_lib.GS_BEST:_lib.GS_BEST + 3] = float("-inf")
+    sh = _lib.GS_HIST + 3 * int(hist_capacity)
+    gs[sh:sh + 3] = gs[_lib.GS_SIGMA:_lib.GS_SIGMA + 3]
+    return gs.to(device)
+
+
+def generation_end(eval_out, gstate, hist_capacity, *, agent_step_limit=None, reference_compat=True,
+                   adaptive=False, sigma_max=0.5, sigma_min=0.001, early_stopping=False, min_delta=0.1,
+                   patience=300):
+    """End-of-generation bookkeeping on the device (evaluation mean, reward history, adaptive sigma,
+    early-stopping counters); see ``cev_generation_end_f64``."""
+    dev = _need_cuda(eval_out, gstate)
+    if eval_out.dtype != torch.float64 or gstate.dtype != torch.float64:
+        raise _lib.CevError("generation_end: eval_out and gstate must be float64")
+    n_games = eval_out.numel() // _lib.ROLLOUT_OUT_DIM
+    check(_call("cev_generation_end_f64", _h(dev), _ptr(eval_out), n_games,
+                -1 if agent_step_limit is None else int(agent_step_limit), int(bool(reference_compat)),
+                _ptr(gstate), int(hist_capacity), int(bool(adaptive)), float(sigma_max), float(sigma_min),
+                int(bool(early_stopping)), float(min_delta), int(patience), _stream(dev)),
+          "cev_generation_end_f64")
+    return gstate
 
 
 def axpy(a, x, y):
@@ -298,9 +392,11 @@ def axpy(a, x, y):
 
 def diversity_dist(pop, ref, in_dim, *, out=None):
     """K7: fp32[P] distances || pop[i] - ref || over the Linear parameters."""
-    dev = _need_cuda(pop, ref, out)
+    dev = _need_cuda(ref, out, pop if pop.numel() else None)
     if out is None:
         out = torch.empty(pop.shape[0], dtype=torch.float32, device=dev)
+    if pop.shape[0] == 0:
+        return out
     check(_call("cev_diversity_dist_f32", _h(dev), _ptr(pop), pop.shape[0], pop.stride(0),
                                         _ptr(ref), int(in_dim), _ptr(out), _stream(dev)),
           "cev_diversity_dist_f32")

@@ -94,5 +94,13 @@ class DeviceMPEEnv:
         self.pending = None
         return self.stream.draw(n)
 
+    def state_dict(self):
+        """The PCG64 bit-generator state (checkpoint / resume keeps the reset stream in step)."""
+        return {"bit_generator": self.stream.rng.bit_generator.state}
+
+    def load_state_dict(self, sd):
+        self.stream.rng.bit_generator.state = sd["bit_generator"]
+        self.pending = None
+
     def close(self):
         pass

@@ -73,8 +73,10 @@ typedef struct {
                                     under play_MPE's agent-step limit
                                     (utils/game_logic_functions.py:127,195) */
     int32_t integrate_pos_first; /* SURVEY.md Appendix A.4 switch (1 = PettingZoo >= 1.24) */
-    int32_t variant;             /* 0 auto, 1 generic kernel, 2 cluster kernel (member weights resident in
-                                    shared memory), 3 lockstep kernels (opponent forwards on tcgen05) */
+    int32_t variant;             /* 0 auto (from THIS call's P*K*E), 1 generic kernel, 2 cluster kernel (member
+                                    weights resident in shared memory), 3 lockstep kernels (opponent forwards on
+                                    tcgen05).  A sharded caller passes the variant chosen for the GLOBAL
+                                    population (cev_mpe_rollout_plan) so every rank runs the same arithmetic. */
     int32_t reserved;
 } cev_rollout_cfg;
 
@@ -98,6 +100,26 @@ int cev_mpe_rollout_f32(cev_handle* h, int member_seat,
                         const double* init, int init_shared, int E,
                         const cev_rollout_cfg* cfg,
                         double* out, int32_t* status, cev_stream stream);
+
+/*
+ * K1, lockstep kernels (variant 3) with parity instrumentation: the same launches as
+ * cev_mpe_rollout_f32, plus -- each optional -- teacher forcing and traces, laid out
+ * [n_cycles][3 seats][N = P*K*E episodes]:
+ *   forced_actions  int32: actions the world step replays instead of the networks' own
+ *                   (the oracle's trace: FCNetwork.forward is then compared logit by logit on
+ *                   identical observations, MPE/fcnetwork.py:37-70)
+ *   logits_out      fp32 [..][5]: the logits behind every decision (member forward on the FP32
+ *                   pipe, opponent forwards on tcgen05)
+ *   actions_out     int32: the networks' own first-max decisions (MPE/fcnetwork.py:73-90)
+ */
+int cev_mpe_rollout_trace_f32(cev_handle* h, int member_seat,
+                              const float* members, int P, int64_t member_pitch,
+                              const float* opp_a, int64_t opp_a_pitch,
+                              const float* opp_b, int64_t opp_b_pitch, int K,
+                              const double* init, int init_shared, int E,
+                              const cev_rollout_cfg* cfg,
+                              const int32_t* forced_actions, float* logits_out, int32_t* actions_out,
+                              double* out, int32_t* status, cev_stream stream);
 
 /*
  * Which kernel a structured rollout of this shape uses (variant 0 = the library's choice) and
@@ -150,21 +172,38 @@ int cev_fc_forward_f32(cev_handle* h, const float* rows, int64_t pitch, int in_d
  * member=c, param).  noise_out (optional) receives the N(0,1) draws.
  */
 int cev_ga_repopulate_f32(cev_handle* h, const float* elites, int E,
-                          int D, int64_t pitch, float sigma,
+                          int D, int64_t pitch, float sigma, const double* sigma_dev,
                           uint64_t seed, int role, uint32_t gen,
                           int64_t row0, int64_t n_rows,
                           float* out, float* noise_out, cev_stream stream);
+/*
+ * `sigma_dev` (K3, K5, K6; may be NULL): when non-NULL the mutation power is read from this DEVICE
+ * fp64 scalar (rounded to fp32 like float(sigma)) instead of the by-value `sigma`: the slot of the
+ * generation state cev_generation_end_f64 adapts, so no scalar leaves the device between generations.
+ */
 
-/* gather rows: dst[i] = src[idx[i]] (elite / HoF extraction, genetic_algorithm.py:240-275) */
+/*
+ * Elite / Hall-of-Fame extraction (genetic_algorithm.py:240-275): dst[i] = src[idx[i] - row0] when the
+ * GLOBAL row id idx[i] (device int64) lies in this rank's block [row0, row0 + n_local), zeros
+ * otherwise -- summed over ranks that is the HoF / elite broadcast, with the indices never leaving the
+ * device.  n_local < 0: plain gather, dst[i] = src[idx[i] - row0].
+ */
 int cev_gather_rows_f32(cev_handle* h, const float* src, int64_t pitch,
-                        const int64_t* idx, int n, float* dst, cev_stream stream);
+                        const int64_t* idx, int n, int64_t row0, int64_t n_local,
+                        float* dst, cev_stream stream);
 
 /*
  * K4 -- selection.  Replaces np.argsort(fitness)[::-1][:E]
- * (genetic_algorithm.py:223-234): indices of the k largest, descending,
- * ties -> lower index (defined; the reference's sort is unstable).
+ * (genetic_algorithm.py:223-234): indices of the k largest, descending; any k <= P.
+ *   order 0: ties -> lower index, NaN last (= argsort(-f, kind="stable"))
+ *   order 1: the reference's expression evaluated with a STABLE ascending sort: ties -> HIGHER
+ *            index, NaN first.  NumPy's default kind leaves the order of
+ *            ties unspecified (x86-simd-sort on AVX2 / AVX-512 hosts), so this is one admissible
+ *            reference outcome, the one of its scalar insertion-sort path.
  */
-int cev_select_topk_f64(cev_handle* h, const double* fitness, int64_t P, int k,
+#define CEV_ORDER_STABLE_DESC 0
+#define CEV_ORDER_REFERENCE 1
+int cev_select_topk_f64(cev_handle* h, const double* fitness, int64_t P, int k, int order,
                         int64_t* idx_out, cev_stream stream);
 
 /*
@@ -173,7 +212,7 @@ int cev_select_topk_f64(cev_handle* h, const double* fitness, int64_t P, int k,
  * parameters only (LayerNorm rows copied), Philox(seed, ES, role, gen, member).
  */
 int cev_es_perturb_f32(cev_handle* h, const float* theta, int in_dim,
-                       float sigma, uint64_t seed, int role, uint32_t gen,
+                       float sigma, const double* sigma_dev, uint64_t seed, int role, uint32_t gen,
                        int64_t row0, int64_t n_rows, int64_t pitch,
                        float* out, float* noise_out, cev_stream stream);
 
@@ -184,8 +223,8 @@ int cev_es_perturb_f32(cev_handle* h, const float* theta, int in_dim,
  * as cev_es_perturb_f32.
  */
 int cev_es_perturb_prefix_f32(cev_handle* h, const float* theta, int64_t d_pert, int64_t d_total, float sigma,
-                              uint64_t seed, int role, uint32_t gen, int64_t row0, int64_t n_rows, int64_t pitch,
-                              float* out, cev_stream stream);
+                              const double* sigma_dev, uint64_t seed, int role, uint32_t gen, int64_t row0,
+                              int64_t n_rows, int64_t pitch, float* out, cev_stream stream);
 
 /*
  * K6 -- ES fitness-weighted update.  Replaces compute_weight_update
@@ -196,7 +235,7 @@ int cev_es_perturb_prefix_f32(cev_handle* h, const float* theta, int64_t d_pert,
  * rank's members are all-reduced by the caller.
  */
 int cev_es_update_f32(cev_handle* h, const double* fitness, int in_dim,
-                      float sigma, float lr, int64_t n_total,
+                      float sigma, const double* sigma_dev, float lr, int64_t n_total,
                       uint64_t seed, int role, uint32_t gen,
                       int64_t row0, int64_t n_rows,
                       float* delta, cev_stream stream);
@@ -210,8 +249,8 @@ int cev_es_update_f32(cev_handle* h, const double* fitness, int in_dim,
  * any row layout of `pitch` floats (DeepQN rows): unperturbed entries equal theta and contribute zeros.
  */
 int cev_es_update_members_f32(cev_handle* h, const double* fitness, const float* members, int64_t pitch,
-                              const float* theta, int in_dim, float sigma, float lr, int64_t n_total,
-                              int64_t n_rows, float* delta, cev_stream stream);
+                              const float* theta, int in_dim, float sigma, const double* sigma_dev, float lr,
+                              int64_t n_total, int64_t n_rows, float* delta, cev_stream stream);
 
 /* theta[j] += delta[j] (evolutionary_strategy.py:259-265) */
 int cev_axpy_f32(cev_handle* h, float a, const float* x, float* y, int64_t n, cev_stream stream);
@@ -224,6 +263,41 @@ int cev_axpy_f32(cev_handle* h, float a, const float* x, float* y, int64_t n, ce
 int cev_diversity_dist_f32(cev_handle* h, const float* pop, int64_t n_rows,
                            int64_t pitch, const float* ref, int in_dim,
                            float* dist, cev_stream stream);
+
+/*
+ * Per-member statistics of the perturbable weights.  Replaces MPEAgent.log_weight_statistics
+ * (MPE/mpe_agent.py:30-50; called once per perturbed member from Agent.mutate_ES, agent.py:66):
+ * out fp32 [n_rows, 4] = (mean, min, max, population std) of get_perturbable_weights().
+ */
+int cev_weight_stats_f32(cev_handle* h, const float* rows, int64_t n_rows, int64_t pitch, int in_dim,
+                         float* out, cev_stream stream);
+
+/*
+ * End of a generation, on the device.  Replaces the tail of the training loops:
+ * the mean of the evaluation games (evaluate_current_weights, genetic_algorithm.py:12-29,
+ * evolutionary_strategy.py:22-59), rewards_over_generations.append, the adaptive mutation power
+ * (genetic_algorithm.py:323-345, evolutionary_strategy.py:292-316; NumPy's mean order, agent_0
+ * growing from sigma_agent_1 * 1.2) and the early-stopping counters
+ * (evolutionary_strategy.py:318-354).
+ *
+ * eval_out: fp64 [n_games, 4], the rollout output of the evaluation games.  gstate: DEVICE fp64
+ * array of cev_generation_state_doubles(hist_capacity) entries, roles in the order agent_0, agent_1,
+ * adversary_0:
+ */
+#define CEV_GS_GEN 0          /* generations finished so far                                   */
+#define CEV_GS_SIGMA 1        /* [3] current mutation power (the sigma_dev slots of K3/K5/K6)  */
+#define CEV_GS_BEST 4         /* [3] best evaluation reward (early stopping), init -inf        */
+#define CEV_GS_STALE 7        /* [3] generations without improvement                           */
+#define CEV_GS_STOP 10        /* 0, or 1 + role index of the role that triggered early stopping */
+#define CEV_GS_STOP_GEN 11
+#define CEV_GS_LAST_EVAL 12   /* [3] evaluation rewards of the generation just finished         */
+#define CEV_GS_HIST 16        /* [hist_capacity][3] evaluation rewards, then [hist_capacity+1][3]
+                                 mutation-power history (entry 0 = the initial sigma)          */
+int cev_generation_state_doubles(int hist_capacity);
+int cev_generation_end_f64(cev_handle* h, const double* eval_out, int n_games, int agent_step_limit,
+                           int reference_compat, double* gstate, int hist_capacity, int adaptive,
+                           double sigma_max, double sigma_min, int early_stopping, double min_delta,
+                           int patience, cev_stream stream);
 
 /*
  * K2 -- grouped per-member DeepQN forward.  Replaces DeepQN.forward

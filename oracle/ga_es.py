@@ -9,14 +9,19 @@ from __future__ import annotations
 import numpy as np
 
 
-def select_topk(fitness, k):
+def select_topk(fitness, k, order=0):
     """Indices of the ``k`` largest fitness values, descending.
 
     Follows genetic_algorithm.py:223-234 (``np.argsort(f)[::-1][:E]``).  The
-    reference's sort is unstable, so ties are implementation-defined there;
-    this build DEFINES ties -> lower index first which
-    is ``argsort(-f, kind='stable')``.  NaN cannot occur (forward raises)."""
+    reference's default sort is unstable for large arrays, so ties are
+    implementation-defined there.  ``order=0`` DEFINES ties -> lower index first
+     = ``argsort(-f, kind='stable')``, NaN last.
+    ``order=1`` is the reference's expression with a STABLE ascending sort --
+    what NumPy's insertion sort does for n <= 16, the sizes of the reference's own
+    runs: ties -> higher index first, NaN first (Appendix C #18)."""
     f = np.asarray(fitness, dtype=np.float64)
+    if order == 1:
+        return np.argsort(f, kind="stable")[::-1][:k].astype(np.int64)
     return np.argsort(-f, kind="stable")[:k].astype(np.int64)
 
 
@@ -102,3 +107,84 @@ def adaptive_sigma(sig0, sig1, sigadv, hist0, hist1, histadv, gen, smin, smax):
     else:
         sigadv = max(sigadv * 0.95, smin)
     return sig0, sig1, sigadv
+
+
+def reward_slots(out, agent_step_limit=None, reference_compat=True):
+    """play_MPE's three return slots from the physical sums (sum_good, last_good, sum_adv)
+    (utils/game_logic_functions.py:179-190)."""
+    sg, lg, sa = out[..., 0], out[..., 1], out[..., 2]
+    if not reference_compat:
+        return sg, sg, sa
+    L = 75 if agent_step_limit is None else int(min(75, max(0, int(agent_step_limit))))
+    nc = L // 3
+    if nc == 0:
+        z = np.zeros_like(sg)
+        return z, sa, z
+    n_adv = -(-L // 3)
+    n_a0 = -(-(L - 1) // 3)
+    slot_adv = sg if n_adv - 1 >= nc else sg - lg
+    slot_a0 = sg if n_a0 - 1 >= nc else sg - lg
+    return slot_a0, sa, slot_adv
+
+
+# slots of the device generation state (CEV_GS_* in include/coevonet_b200.h)
+GS_GEN, GS_SIGMA, GS_BEST, GS_STALE, GS_STOP, GS_STOP_GEN, GS_LAST_EVAL, GS_HIST = 0, 1, 4, 7, 10, 11, 12, 16
+
+
+def generation_state(sigmas, hist_capacity):
+    gs = np.zeros(GS_HIST + 3 * hist_capacity + 3 * (hist_capacity + 1))
+    gs[GS_SIGMA:GS_SIGMA + 3] = sigmas
+    gs[GS_BEST:GS_BEST + 3] = -np.inf
+    gs[GS_HIST + 3 * hist_capacity:GS_HIST + 3 * hist_capacity + 3] = sigmas
+    return gs
+
+
+def generation_end(eval_out, gs, hist_capacity, agent_step_limit=None, reference_compat=True, adaptive=False,
+                   sigma_max=0.5, sigma_min=0.001, early_stopping=False, min_delta=0.1, patience=300):
+    """Tail of a training-loop iteration, restated with the reference's own expressions:
+    evaluate_current_weights' running sums / 10 (genetic_algorithm.py:12-29), the reward lists,
+    the adaptive mutation power (genetic_algorithm.py:323-345 == evolutionary_strategy.py:292-316,
+    np.mean on Python-float lists) and the early-stopping counters (evolutionary_strategy.py:318-354).
+    ``gs`` is updated in place (same slots as the device array)."""
+    out = np.asarray(eval_out, dtype=np.float64).reshape(-1, 4)
+    gen = int(gs[GS_GEN])
+    tot = [0.0, 0.0, 0.0]
+    for g in range(out.shape[0]):
+        s0, s1, sadv = reward_slots(out[g], agent_step_limit, reference_compat)
+        tot[0] += float(s0)
+        tot[1] += float(s1)
+        tot[2] += float(sadv)
+    ev = [t / out.shape[0] for t in tot]
+    hist = gs[GS_HIST:GS_HIST + 3 * hist_capacity].reshape(hist_capacity, 3)
+    shist = gs[GS_HIST + 3 * hist_capacity:].reshape(hist_capacity + 1, 3)
+    if gen < hist_capacity:
+        hist[gen] = ev
+    gs[GS_LAST_EVAL:GS_LAST_EVAL + 3] = ev
+    if adaptive:
+        lists = [list(hist[:gen + 1, r]) for r in range(3)]
+        sig = adaptive_sigma(gs[GS_SIGMA], gs[GS_SIGMA + 1], gs[GS_SIGMA + 2], lists[0], lists[1], lists[2], gen,
+                             sigma_min, sigma_max)
+        gs[GS_SIGMA:GS_SIGMA + 3] = sig
+    if gen + 1 <= hist_capacity:
+        shist[gen + 1] = gs[GS_SIGMA:GS_SIGMA + 3]
+    if early_stopping and gs[GS_STOP] == 0:
+        for r in range(3):
+            if ev[r] > gs[GS_BEST + r] + min_delta:
+                gs[GS_BEST + r] = ev[r]
+                gs[GS_STALE + r] = 0
+            else:
+                gs[GS_STALE + r] += 1
+        for r in range(3):
+            if gs[GS_STALE + r] >= patience:
+                gs[GS_STOP] = 1 + r
+                gs[GS_STOP_GEN] = gen
+                break
+    gs[GS_GEN] = gen + 1
+    return gs
+
+
+def weight_stats(rows, pert_idx):
+    """MPEAgent.log_weight_statistics (MPE/mpe_agent.py:30-50): mean, min, max, std (ddof 0)
+    of every row's perturbable weights."""
+    w = np.asarray(rows, dtype=np.float32)[:, pert_idx]
+    return np.stack([w.mean(axis=1), w.min(axis=1), w.max(axis=1), w.std(axis=1)], axis=1)

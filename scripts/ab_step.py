@@ -13,11 +13,11 @@ torch.manual_seed(0)
 theta = {r: FCNetwork(layout.OBS_DIM[r], 5, "float32").flat_row() for r in bench.ROLES}
 eng = engine.ESEngine(args, dev, theta)
 def run(n=8):
-    for _ in range(2): eng.step()
+    for _ in range(2): eng.step(sync=False)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(n): eng.step()
+    for _ in range(n): eng.step(sync=False)
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
 for rep in range(2):

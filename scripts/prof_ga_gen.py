@@ -25,14 +25,12 @@ def timed(name, fn):
     print(f"  {name:28s} {1e3 * (time.perf_counter() - t0):8.2f} ms", flush=True)
     return r
 
-for g in range(2):
+for g in range(3):
     print(f"generation {g} (P={P}, init={init_mode})")
     t0 = time.perf_counter()
-    for role in engine.ROLES:
-        timed(f"evaluate_role({role})", lambda: eng.evaluate_role(role))
-    for role in engine.ROLES:
-        timed(f"select_and_repopulate({role})", lambda: eng.select_and_repopulate(role))
+    timed("evaluate (3 roles, 3 streams)", eng.evaluate)
+    timed("select_and_repopulate (3 roles)", eng.select_and_repopulate)
     best = {r: eng.elites[r][0] for r in engine.ROLES}
-    timed("evaluate_triple", lambda: eng.evaluate_triple(best["agent_0"], best["agent_1"], best["adversary_0"]))
+    timed("eval games + generation_end", lambda: eng._finish_generation(best["agent_0"], best["agent_1"], best["adversary_0"]))
     eng.gen += 1
     print(f"  total {1e3 * (time.perf_counter() - t0):.1f} ms")

@@ -33,3 +33,22 @@ def golden():
     def load(name):
         return np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
     return load
+
+
+def parity_report(key, value):
+    """Record an observed parity figure (match rates, agreeing generations, max logit error) next to the
+    test log: gpurun_out/parity_report.json on the GPU box; copied to profiles/ when it is to be judged."""
+    import json
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out_dir, exist_ok=True)
+        path = os.path.join(out_dir, "parity_report.json")
+        data = {}
+        if os.path.isfile(path):
+            with open(path) as f:
+                data = json.load(f)
+        data[key] = value
+        with open(path, "w") as f:
+            json.dump(data, f, indent=1, sort_keys=True)
+    except OSError:
+        pass

@@ -23,6 +23,19 @@ def raise_on_status(status):
         raise ValueError("\n\t Warning: output contains inf or NaN")
 
 
+def generation_state(sigmas, hist_capacity, device):
+    return torch.from_numpy(ga_es.generation_state([float(x) for x in sigmas], int(hist_capacity)))
+
+
+def generation_end(eval_out, gstate, hist_capacity, **kw):
+    ga_es.generation_end(eval_out.numpy(), gstate.numpy(), int(hist_capacity), **kw)   # in place (shared memory)
+    return gstate
+
+
+def weight_stats(rows, in_dim, *, out=None):
+    return torch.from_numpy(ga_es.weight_stats(rows.numpy(), olayout.fc_perturbable_index(in_dim)).astype(np.float32))
+
+
 def mpe_rollout(member_role, members, opp_a, opp_b, init, *, n_cycles=MAX_CYCLES, pos_first=True,
                 init_shared=False, variant=0, out=None, status=None):
     seat = layout.SEAT_OF[member_role] if isinstance(member_role, str) else int(member_role)
@@ -57,16 +70,25 @@ def diversity_dist(pop, ref, in_dim, *, out=None):
     return torch.from_numpy(d)
 
 
-def select_topk(fitness, k):
-    return torch.from_numpy(ga_es.select_topk(fitness.numpy(), k))
+def select_topk(fitness, k, order=0):
+    return torch.from_numpy(ga_es.select_topk(fitness.numpy(), k, order))
 
 
-def gather_rows(src, idx, *, out=None):
-    return src[idx].clone()
+def gather_rows(src, idx, *, row0=0, n_local=None, out=None):
+    pitch = src.shape[-1]
+    res = torch.zeros((idx.shape[0], pitch), dtype=torch.float32) if out is None else out
+    for i, g in enumerate(idx.tolist()):
+        s = g - row0
+        if n_local is None or 0 <= s < n_local:
+            res[i] = src[s]
+        else:
+            res[i] = 0
+    return res
 
 
 def ga_repopulate(elites, dim, sigma, seed, role, gen, row0, n_rows, *, out=None, noise_out=None):
     role_id = layout.ROLE_ID[role] if isinstance(role, str) else int(role)
+    sigma = float(sigma)
     E, pitch = elites.shape
     res = torch.zeros((n_rows, pitch), dtype=torch.float32) if out is None else out
     el = elites.numpy()
@@ -84,6 +106,7 @@ def ga_repopulate(elites, dim, sigma, seed, role, gen, row0, n_rows, *, out=None
 
 def es_perturb(theta, in_dim, sigma, seed, role, gen, row0, n_rows, *, out=None, noise_out=None):
     role_id = layout.ROLE_ID[role] if isinstance(role, str) else int(role)
+    sigma = float(sigma)
     D = layout.fc_dim(in_dim)
     pidx = olayout.fc_perturbable_index(in_dim)
     z = philox.normals(seed, philox.KIND_ES, role_id, gen, np.arange(row0, row0 + n_rows), D)
@@ -96,6 +119,7 @@ def es_perturb(theta, in_dim, sigma, seed, role, gen, row0, n_rows, *, out=None,
 
 def es_update(fitness, in_dim, sigma, lr, n_total, seed, role, gen, row0, *, out=None):
     role_id = layout.ROLE_ID[role] if isinstance(role, str) else int(role)
+    sigma = float(sigma)
     D = layout.fc_dim(in_dim)
     pidx = olayout.fc_perturbable_index(in_dim)
     n = fitness.shape[0]
@@ -105,16 +129,25 @@ def es_update(fitness, in_dim, sigma, lr, n_total, seed, role, gen, row0, *, out
     coef = np.float32(lr / (n_total * sigma))
     delta = np.zeros(layout.fc_pitch(in_dim), dtype=np.float32)
     delta[pidx] = coef * (noise.T @ f)
-    return torch.from_numpy(delta)
+    res = torch.from_numpy(delta)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
 
 
 def es_update_members(fitness, members, theta, in_dim, sigma, lr, n_total, *, out=None):
     """K6 from the materialised members: sigma*z_i taken as members[i] - theta (the engine's default)."""
+    sigma = float(sigma)
     pitch = members.shape[1]
     noise = (members.numpy() - theta.numpy()[:pitch]).astype(np.float32)
     f = fitness.numpy().astype(np.float32)
     coef = np.float32(lr / (n_total * sigma))
-    return torch.from_numpy((coef * (noise.T @ f)).astype(np.float32))
+    res = torch.from_numpy((coef * (noise.T @ f)).astype(np.float32))
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
 
 
 def axpy(a, x, y):

@@ -135,3 +135,60 @@ def test_es_two_ranks_match_one_rank():
         # |fitness| ~ 40 and lr/(n sigma) = 0.33 over 6 members): 1e-5 absolute on a delta of magnitude ~5
         np.testing.assert_allclose(o["theta"], single["theta"], rtol=0, atol=3e-5)
     assert np.array_equal(two[0]["theta"], two[1]["theta"])                              # replicas agree
+
+
+def _run_unseeded(rank, world, port, q):
+    """Two ranks whose torch generators DIFFER (what an unseeded torchrun launch gives): the base agents
+    must still come out identical -- rank 0's -- on both (evolutionary_strategy.py:222-233)."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    torch.set_num_threads(1)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle_backend
+    from coevonet_b200 import engine, layout
+    from coevonet_b200.MPE.fcnetwork import FCNetwork
+    comm = engine.Comm()
+    torch.manual_seed(1000 + 17 * rank)
+    expect_first = FCNetwork(10, 5, "float32").flat_row() if rank == 0 else None
+    torch.manual_seed(1000 + 17 * rank)
+    # (a) the drivers' path: generator state of rank 0 on every rank, then the reference's constructors
+    engine.sync_torch_rng(comm)
+    synced = {r: FCNetwork(layout.OBS_DIM[r], 5, "float32").flat_row() for r in ROLES}
+    # (b) the engine's own guard: rows that differ per rank are replaced by rank 0's
+    torch.manual_seed(5 + rank)
+    different = {r: FCNetwork(layout.OBS_DIM[r], 5, "float32").flat_row() for r in ROLES}
+    args = _args("ES", 4)
+    eng = engine.ESEngine(args, "cpu", different, kernels=oracle_backend, comm=comm)
+    ev = eng.step()
+    q.put(dict(rank=rank, synced=np.stack([synced[r].numpy()[:3000] for r in ROLES]),
+               theta=np.stack([eng.theta[r].numpy()[:3000] for r in ROLES]), ev=np.asarray(ev),
+               first=None if expect_first is None else expect_first.numpy()[:3000]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_unseeded_ranks_start_from_rank0_state():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_run_unseeded, args=(r, 2, 29617, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = sorted([q.get(timeout=300) for _ in range(2)], key=lambda o: o["rank"])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert np.array_equal(outs[0]["synced"], outs[1]["synced"])          # same founders on both ranks
+    assert np.array_equal(outs[0]["synced"][0], outs[0]["first"])         # and they are what rank 0 alone draws
+    assert np.array_equal(outs[0]["theta"], outs[1]["theta"])            # engine guard: replicas agree after a step
+    assert np.array_equal(outs[0]["ev"], outs[1]["ev"])
+
+
+def test_empty_shard_contributes_nothing():
+    """population < world size: ranks with no rows must run -- host-side shapes."""
+    sys.path.insert(0, ROOT)
+    from coevonet_b200.engine import Shard
+    s = [Shard(3, r, 8) for r in range(8)]
+    assert [x.n_local for x in s] == [1, 1, 1, 0, 0, 0, 0, 0]
+    assert all(x.row0 == 3 for x in s[3:])

@@ -15,7 +15,14 @@ import numpy as np
 import pytest
 import torch
 
+from conftest import parity_report
+
 pytestmark = pytest.mark.gpu
+
+#: generations of the golden runs that agreed member by member on the B200 (observed, round 2); a
+#: regression below these numbers fails
+GA_AGREED_OBSERVED = 1
+ES_AGREED_OBSERVED = 1
 
 ROLES = ("agent_0", "agent_1", "adversary_0")
 RTOL = 1e-4
@@ -64,15 +71,16 @@ def test_ga_train_matches_reference_run(golden, tmp_path):
             ok = ok and match.all()
             assert abs(hist[gen]["diversity"][role] - g["diversity"][gen, ri]) <= 1e-3 * max(1, abs(g["diversity"][gen, ri])) or not ok
             if match.all():
-                want_ids = np.argsort(-want, kind="stable")[:args.elites_number]
+                want_ids = np.argsort(want, kind="stable")[::-1][:args.elites_number]   # K4, reference order
                 assert np.array_equal(hist[gen]["elite_ids"][role], want_ids)
         if not ok:
             break
         np.testing.assert_allclose(hist[gen]["evals"], g["evals"][gen], rtol=RTOL, atol=1e-9)
         np.testing.assert_allclose([hist[gen]["sigma"][r] for r in ROLES], g["sigma_used"][gen], rtol=1e-12)
         agreed += 1
-    assert agreed >= 1, "not even generation 0 agreed with the reference run"
     print(f"GA: {agreed}/{gens} generations agree with the reference run")
+    parity_report("ga_run_generations_agreed", f"{agreed}/{gens}")
+    assert agreed >= GA_AGREED_OBSERVED, f"only {agreed}/{gens} generations agreed with the reference run"
     if agreed == gens:
         got_sigma = [args.mutation_power_agent_0, args.mutation_power_agent_1, args.mutation_power_adversary]
         np.testing.assert_allclose(got_sigma, g["final_sigma"], rtol=1e-12)
@@ -113,8 +121,9 @@ def test_es_train_matches_reference_run(golden, tmp_path):
             assert abs(hist[gen]["diversity"][role] - g["diversity"][gen, ri]) <= 1e-3 * max(1, g["diversity"][gen, ri])
         np.testing.assert_allclose(hist[gen]["evals"], g["evals"][gen], rtol=RTOL, atol=1e-9)
         agreed += 1
-    assert agreed >= 1, "not even generation 0 agreed with the reference run"
     print(f"ES: {agreed}/{gens} generations agree with the reference run")
+    parity_report("es_run_generations_agreed", f"{agreed}/{gens}")
+    assert agreed >= ES_AGREED_OBSERVED, f"only {agreed}/{gens} generations agreed with the reference run"
     if agreed == gens:
         for ri, m in enumerate((a0, a1, adv)):
             w = m.model.get_perturbable_weights()
