@@ -319,9 +319,10 @@ extern "C" int cev_deepqn_forward(cev_handle* h, const float* members, int P, in
     float* y3 = p.act3 + per * 3136;          // conv3's pre-BatchNorm output (tensor-core conv path)
     p.logits = logits;
     p.actions = actions;
-    // fully-connected stage: tcgen05 (TF32, default) or the fp32 CUDA-core loop (COEVONET_DQN_FC=fp32);
-    // convolution stack: tcgen05 implicit GEMM (3xTF32, default with the tensor-core fc stage) or the fp32
-    // CUDA-core kernel (COEVONET_DQN_CONV=fp32, and always with COEVONET_DQN_FC=fp32: the tight-parity path)
+    // fully-connected stage: tcgen05 (3xTF32, fp32-level accuracy; default) or the fp32 CUDA-core loop
+    // (COEVONET_DQN_FC=fp32); convolution stack: tcgen05 implicit GEMM (3xTF32, default with the tensor-core fc
+    // stage) or the fp32 CUDA-core kernel (COEVONET_DQN_CONV=fp32, and always with COEVONET_DQN_FC=fp32).
+    // Both stages meet the same 2e-5 tolerance against the reference's fp32 forward.
     const char* fc_env = getenv("COEVONET_DQN_FC");
     const bool use_tc = !(fc_env && strcmp(fc_env, "fp32") == 0);
     const char* conv_env = getenv("COEVONET_DQN_CONV");

@@ -1121,9 +1121,12 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
         cuuint64_t strides[2] = {(cuuint64_t)H1 * 4, (cuuint64_t)p.member_pitch * 4};
         cuuint32_t box[3] = {LS_TILE_K, LS_TILE_ROWS, 1};
         cuuint32_t estr[3] = {1, 1, 1};
+        static const int l2p = getenv("CEV_LS_L2P") ? atoi(getenv("CEV_LS_L2P")) : 128;
         CUresult r = encode(&map_w2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.members + om.fc2w), dims,
                             strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
-                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                            l2p == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                       : (l2p == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B),
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             set_error("rollout_lockstep: cuTensorMapEncodeTiled(member fc2) failed with %d", (int)r);
             return CEV_ERR_CUDA;

@@ -1,12 +1,12 @@
 """K2 parity: grouped per-member DeepQN forward (through the C ABI) vs the
 reference's own DeepQN.forward outputs (tests/golden/deepqn.npz) and the oracle.
 
-Two fully-connected stages are tested:
-* ``fp32`` (COEVONET_DQN_FC=fp32): CUDA-core fp32, different summation order only
-  -> 2e-5 absolute on logits of magnitude ~0.2;
-* ``tc`` (default): tcgen05 kind::tf32 (10-bit mantissa inputs, fp32 accumulate over
-  K = 3136) -> 2e-3 absolute; actions are compared where the reference's top-2 logit
-  gap exceeds that tolerance."""
+Two fully-connected stages are tested, both to the SAME fp32-level tolerance (2e-5 absolute on logits of
+magnitude ~0.2: summation order only):
+* ``tc`` (default): tcgen05 kind::tf32 with every product issued three times (3xTF32: lo.hi + hi.lo + hi.hi,
+  fp32 accumulation over K = 3136), W1 as the M-side operand;
+* ``fp32`` (COEVONET_DQN_FC=fp32): the CUDA-core fp32 stage.
+Actions are compared where the reference's top-2 logit gap exceeds twice the tolerance."""
 import os
 
 import numpy as np
@@ -26,7 +26,7 @@ def _pad(rows, c_in, n_act):
     return torch.from_numpy(out).cuda()
 
 
-FC_MODES = {"fp32": 2e-5, "tc": 2e-3}
+FC_MODES = {"fp32": 2e-5, "tc": 2e-5}
 
 
 @pytest.fixture(params=sorted(FC_MODES))
@@ -59,7 +59,7 @@ def test_deepqn_forward_matches_reference_golden(golden, fc_mode, c_in, n_act):
 def test_deepqn_many_frames_and_members_vs_oracle(fc_mode):
     from coevonet_b200 import ops
     tol = FC_MODES[fc_mode]
-    c_in, n_act, P, B = 4, 6, 3, 13                      # B > frames-per-fc-pass exercises chunking
+    c_in, n_act, P, B = 4, 6, 3, 19                      # B > 16 frames per fc block exercises the frame-block loop
     rows = weights.make_dqn_rows(P, c_in, n_act, 91, bn_jitter=0.1)
     frames = ops.random_frames(5, (P, B, c_in, 84, 84), "cuda")
     logits, actions = ops.deepqn_forward(_pad(rows, c_in, n_act), frames, c_in, n_act)
@@ -83,9 +83,9 @@ def test_deepqn_module_dropin():
     from oracle import layout as olayout
     row = olayout.pack_dqn_state_dict(sd, 4, 6)
     want, _ = odqn.dqn_forward_batch(row[None], x.numpy().astype(np.uint8)[None], 4, 6)
-    np.testing.assert_allclose(got.numpy(), want[0], rtol=0, atol=3e-3)
+    np.testing.assert_allclose(got.numpy(), want[0], rtol=0, atol=3e-5)
     srt = np.sort(want[0, 0])
-    if srt[-1] - srt[-2] > 6e-3:
+    if srt[-1] - srt[-2] > 6e-5:
         assert net.determine_action(x[:1]) == int(np.argmax(want[0, 0]))
 
 

@@ -232,7 +232,11 @@ def test_ranged_gather_weight_stats_and_empty_shards():
     assert torch.equal(lo[1], torch.zeros_like(lo[1])) and torch.equal(hi[0], torch.zeros_like(hi[0]))
     st = ops.weight_stats(rows, 10).cpu().numpy()
     want = ga_es.weight_stats(rows.cpu().numpy()[:, :layout.fc_dim(10)], olayout.fc_perturbable_index(10))
-    np.testing.assert_allclose(st, want, rtol=2e-6, atol=1e-7)
+    # the reference (and its restatement) reduce 138 k fp32 values in fp32 (NumPy's pairwise sums), the kernel
+    # accumulates in fp64: they differ by the reference's own fp32 summation error
+    np.testing.assert_allclose(st[:, 1:3], want[:, 1:3], rtol=0, atol=0)          # min / max are exact
+    np.testing.assert_allclose(st[:, 0], want[:, 0], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(st[:, 3], want[:, 3], rtol=1e-4, atol=0)
     # empty shard (population < world size): every op is a no-op instead of an error
     empty = torch.empty((0, layout.fc_pitch(10)), dtype=torch.float32, device="cuda")
     assert ops.diversity_dist(empty, rows[0], 10).shape == (0,)
