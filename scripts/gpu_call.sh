@@ -1,2 +1,2 @@
 mkdir -p gpurun_out
-for l2p in 256 128 64; do for skip in 0 1; do CEV_LS_L2P=$l2p CEV_LS_SKIP=$skip timeout 120 python scripts/time_ls.py 1024x16 8192x1 2>&1 | sed "s/^/l2p=$l2p /"; done; done
+for PF in 0 2 4 8; do for skip in 0 1; do COEVONET_LIB=$PWD/coevonet_b200/csrc/var/libcev_pf$PF.so CEV_LS_SPLIT=0 CEV_LS_SKIP=$skip timeout 120 python scripts/time_ls.py 1024x16 8192x1 2>&1 | sed "s/^/pf=$PF /"; done; done
