@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("COEVONET_LIB") or os.path.join(_HERE, "csrc", "libcoe
 CEV_OK = 0
 STATUS_NONFINITE = 1
 SEAT = {"adversary_0": 0, "agent_0": 1, "agent_1": 2}
-KIND_ES, KIND_GA, KIND_ENV, KIND_FRAMES = 0, 1, 2, 3
+KIND_ES, KIND_GA, KIND_ENV, KIND_FRAMES, KIND_INIT, KIND_XOVER = 0, 1, 2, 3, 4, 5
 INIT_STATE_DIM = 11
 ROLLOUT_OUT_DIM = 4
 ORDER_STABLE_DESC, ORDER_REFERENCE = 0, 1
@@ -61,7 +61,7 @@ _SIGNATURES = {
                                             POINTER(RolloutCfg), c_void_p, c_void_p, c_void_p]),
     "cev_fc_forward_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64,
                                    c_void_p, c_void_p, c_void_p, c_void_p]),
-    "cev_ga_repopulate_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_float, c_void_p,
+    "cev_ga_repopulate_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_float, c_void_p, c_float,
                                       c_uint64, c_int, c_uint32, c_int64, c_int64,
                                       c_void_p, c_void_p, c_void_p]),
     "cev_gather_rows_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int64, c_int64, c_void_p,
@@ -84,6 +84,9 @@ _SIGNATURES = {
                                        c_void_p, c_void_p]),
     "cev_deepqn_forward": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_int, c_int,
                                    c_int, c_void_p, c_void_p, c_void_p]),
+    "cev_atari_synth_step_u8": (c_int, [c_void_p, c_uint64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p]),
+    "cev_atari_observe_u8": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "cev_fc_init_f32": (c_int, [c_void_p, c_int, c_uint64, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "cev_init_states_f64": (c_int, [c_void_p, c_uint64, c_uint32, c_int64, c_int64, c_void_p, c_void_p]),
     "cev_random_frames_u8": (c_int, [c_void_p, c_uint64, c_int64, c_void_p, c_void_p]),

@@ -20,19 +20,48 @@ __device__ __forceinline__ float pick_sigma(float sigma, const double* __restric
     return sigma_dev ? (float)__ldg(sigma_dev) : sigma;
 }
 
+// Optional uniform crossover (BASELINE north star item 3; the reference's README.md:47 promises crossover, its
+// code has none -- SURVEY.md Appendix C #7 -- so this is an extension, off by default): with probability
+// `xrate` child c takes every parameter from parent A = elites[(c-1) % E] or from a second, different elite B
+// (one Philox bit per parameter), then mutates as usual.  Philox kind CEV_KIND_XOVER: block (0xFFFFFFFF, c, gen)
+// decides (word 0 < xrate * 2^32) and picks the mate (word 1), block (j4, c, gen) holds the four mask bits.
 __global__ void __launch_bounds__(PT) ga_repopulate_kernel(
     const float* __restrict__ elites, int E, int D, int64_t pitch, float sigma_arg,
     const double* __restrict__ sigma_dev,
     const PhiloxKeys keys, uint32_t tag, uint32_t gen, int64_t row0,
+    float xrate, uint32_t xtag,
     float* __restrict__ out, float* __restrict__ noise_out) {
     const float sigma = pick_sigma(sigma_arg, sigma_dev);
     const int64_t r = blockIdx.x;
     const int64_t c = row0 + r;                       // global member id
     const int j4 = blockIdx.y * PT + threadIdx.x;
+    __shared__ int64_t mate_s;
+    int64_t mate = -1;
+    if (xrate > 0.f && E >= 2) {                       // uniform per CTA: one child per blockIdx.x
+        if (threadIdx.x == 0) {
+            int64_t m = -1;
+            if (c != 0) {
+                const U4 y = philox4x32_10(U4{0xFFFFFFFFu, (uint32_t)c, gen, xtag}, keys);
+                if ((double)y.x < (double)xrate * 4294967296.0)
+                    m = ((c - 1) % E + 1 + (int64_t)(y.y % (uint32_t)(E - 1))) % E;
+            }
+            mate_s = m;
+        }
+        __syncthreads();
+        mate = mate_s;
+    }
     if ((int64_t)j4 * 4 >= pitch) return;
     const int64_t parent = (c == 0) ? 0 : (c - 1) % E;
     const float4 pv = *reinterpret_cast<const float4*>(elites + parent * pitch + (int64_t)j4 * 4);
     float p[4] = {pv.x, pv.y, pv.z, pv.w};
+    if (mate >= 0) {
+        const float4 qv = *reinterpret_cast<const float4*>(elites + mate * pitch + (int64_t)j4 * 4);
+        const U4 x = philox4x32_10(U4{(uint32_t)j4, (uint32_t)c, gen, xtag}, keys);
+        if (!(x.x & 1u)) p[0] = qv.x;
+        if (!(x.y & 1u)) p[1] = qv.y;
+        if (!(x.z & 1u)) p[2] = qv.z;
+        if (!(x.w & 1u)) p[3] = qv.w;
+    }
     float z[4] = {0.f, 0.f, 0.f, 0.f};
     if (c != 0) {
         normal4(keys, tag, gen, (uint32_t)c, (uint32_t)j4, z);
@@ -209,17 +238,22 @@ __global__ void __launch_bounds__(PT) diversity_dist_kernel(
     float* __restrict__ dist) {
     const FcOffsets o = fc_offsets(in_dim);
     const int64_t r = blockIdx.x;
-    const float* row = pop + r * pitch;
+    const float4* row = reinterpret_cast<const float4*>(pop + r * pitch);
+    const float4* rf = reinterpret_cast<const float4*>(ref);
     float acc = 0.f;
-    for (int j4 = threadIdx.x; (int64_t)j4 * 4 < pitch; j4 += PT) {
-        const float4 a = *reinterpret_cast<const float4*>(row + (int64_t)j4 * 4);
-        const float4 b = *reinterpret_cast<const float4*>(ref + (int64_t)j4 * 4);
+    // every segment boundary is a multiple of 4 parameters except the end of the row: a float4 is
+    // perturbable or not as a whole; four independent 128-bit loads in flight per thread
+    const int n4 = (int)(pitch / 4);
+#pragma unroll 4
+    for (int j4 = threadIdx.x; j4 < n4; j4 += PT) {
+        const int j = j4 * 4;
+        if (j >= o.total || !fc_is_perturbable(o, j)) continue;
+        const float4 a = __ldcs(row + j4);
+        const float4 b = __ldg(rf + j4);
         const float d[4] = {a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int j = j4 * 4 + i;
-            if (j < o.total && fc_is_perturbable(o, j)) acc = fmaf(d[i], d[i], acc);
-        }
+        for (int i = 0; i < 4; ++i)
+            if (j + i < o.total) acc = fmaf(d[i], d[i], acc);
     }
     __shared__ float red[PT / 32];
 #pragma unroll
@@ -324,19 +358,26 @@ __global__ void __launch_bounds__(PT) weight_stats_kernel(const float* __restric
     const float* row = rows + r * pitch;
     double sum = 0.0, sq = 0.0;
     float mn = CUDART_INF_F, mx = -CUDART_INF_F;
-    for (int j4 = threadIdx.x; (int64_t)j4 * 4 < pitch; j4 += PT) {
-        const float4 a = __ldcs(reinterpret_cast<const float4*>(row + (int64_t)j4 * 4));
+    const int n4 = (int)(pitch / 4);
+#pragma unroll 4
+    for (int j4 = threadIdx.x; j4 < n4; j4 += PT) {
+        const int j = j4 * 4;
+        if (j >= o.total || !fc_is_perturbable(o, j)) continue;
+        const float4 a = __ldcs(reinterpret_cast<const float4*>(row) + j4);
         const float v[4] = {a.x, a.y, a.z, a.w};
+        // fp32 partial sums of one float4, fp64 across float4s (138 k terms per row)
+        float s4 = 0.f, q4 = 0.f;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int j = j4 * 4 + i;
-            if (j < o.total && fc_is_perturbable(o, j)) {
-                sum += (double)v[i];
-                sq = fma((double)v[i], (double)v[i], sq);
+            if (j + i < o.total) {
+                s4 += v[i];
+                q4 = fmaf(v[i], v[i], q4);
                 mn = fminf(mn, v[i]);
                 mx = fmaxf(mx, v[i]);
             }
         }
+        sum += (double)s4;
+        sq += (double)q4;
     }
     __shared__ double rs[PT / 32], rq[PT / 32];
     __shared__ float rmn[PT / 32], rmx[PT / 32];
@@ -592,12 +633,13 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 extern "C" {
 
 int cev_ga_repopulate_f32(cev_handle* h, const float* elites, int E, int D, int64_t pitch, float sigma,
-                          const double* sigma_dev, uint64_t seed, int role, uint32_t gen, int64_t row0,
-                          int64_t n_rows, float* out, float* noise_out, cev_stream stream) {
+                          const double* sigma_dev, float crossover_rate, uint64_t seed, int role, uint32_t gen,
+                          int64_t row0, int64_t n_rows, float* out, float* noise_out, cev_stream stream) {
     CEV_REQUIRE(h != nullptr, "ga_repopulate: null handle");
     if (n_rows == 0) return CEV_OK;                   // an empty shard contributes nothing
     CEV_REQUIRE(elites && out, "ga_repopulate: null pointer");
     CEV_REQUIRE(E >= 1 && D >= 1 && pitch >= D && pitch % 4 == 0, "ga_repopulate: bad E/D/pitch");
+    CEV_REQUIRE(crossover_rate >= 0.f && crossover_rate <= 1.f, "ga_repopulate: crossover_rate must be in [0, 1]");
     CEV_REQUIRE(aligned16(elites) && aligned16(out) && aligned16(noise_out), "ga_repopulate: 16B alignment");
     CEV_REQUIRE(row0 >= 0 && n_rows >= 0 && row0 + n_rows <= 0xFFFFFFFFll, "ga_repopulate: bad row range");
     CEV_GUARD(h);
@@ -605,8 +647,8 @@ int cev_ga_repopulate_f32(cev_handle* h, const float* elites, int E, int D, int6
     split_seed(seed, k0, k1);
     dim3 grid((unsigned)n_rows, (unsigned)((pitch / 4 + PT - 1) / PT));
     ga_repopulate_kernel<<<grid, PT, 0, (cudaStream_t)stream>>>(elites, E, D, pitch, sigma, sigma_dev, philox_keys(k0, k1),
-                                                               noise_tag(CEV_KIND_GA, role), gen, row0, out,
-                                                               noise_out);
+                                                               noise_tag(CEV_KIND_GA, role), gen, row0, crossover_rate,
+                                                               noise_tag(CEV_KIND_XOVER, role), out, noise_out);
     return check_cuda(cudaGetLastError(), "ga_repopulate_kernel");
 }
 

@@ -496,7 +496,8 @@ class GAEngine(_EngineBase):
             self.hof[role] = torch.cat([self.hof[role][1:], elites[0:1]], dim=0).contiguous()
             # next population: row 0 = best unmutated, rows c>=1 = elites[(c-1)%E] + sigma*N(0,1)
             self.k.ga_repopulate(elites, layout.fc_dim(in_dim), self.sigma_dev(role), self.seed, role, self.gen,
-                                 self.shard.row0, self.shard.n_local, out=self.pop[role])
+                                 self.shard.row0, self.shard.n_local, out=self.pop[role],
+                                 crossover_rate=float(getattr(a, "crossover_rate", 0.0)))
 
     def step(self, sync=True):
         """One generation.  ``sync=True`` returns the evaluation triple (one host read);

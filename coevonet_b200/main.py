@@ -70,6 +70,9 @@ def parse_arguments(argv=None):
                         "reference overwrites (they never reach the fitness; skipped by default)")
     p.add_argument("--seed", type=int, default=1870300, help="run seed of the Philox noise streams")
     p.add_argument("--torch_seed", type=int, default=None, help="torch.manual_seed for the founders")
+    p.add_argument("--crossover_rate", type=float, default=0.0,
+                   help="GA extension (the reference has no crossover, README.md:47 vs code): probability that a "
+                        "child is a uniform crossover of two elites before it is mutated; 0 = reference behaviour")
     p.add_argument("--no_plots", action="store_true")
     p.add_argument("--resume", action="store_true",
                    help="continue from <output_dir>/engine_state_rank<r>.pt (written next to the reference-format "
@@ -133,6 +136,7 @@ class Args:
         self.update_from_members = not a.regenerate_noise
         self.plots = not a.no_plots
         self.resume = a.resume
+        self.crossover_rate = a.crossover_rate
         self.log_member_weight_stats = a.log_member_weight_stats
 
     def print_attributes(self, args=None):

@@ -226,8 +226,10 @@ def _sigma_args(sigma):
     return float(sigma), ctypes.c_void_p(0)
 
 
-def ga_repopulate(elites, dim, sigma, seed, role, gen, row0, n_rows, *, out=None, noise_out=None):
-    """K3: rows [row0, row0+n_rows) of the next GA population."""
+def ga_repopulate(elites, dim, sigma, seed, role, gen, row0, n_rows, *, out=None, noise_out=None,
+                  crossover_rate=0.0):
+    """K3: rows [row0, row0+n_rows) of the next GA population.  ``crossover_rate`` > 0 adds uniform
+    crossover between two elites before the mutation (an extension; 0 = the reference)."""
     dev = _need_cuda(elites, out, noise_out)
     sig, sig_dev = _sigma_args(sigma)
     pitch = elites.stride(0)
@@ -235,7 +237,7 @@ def ga_repopulate(elites, dim, sigma, seed, role, gen, row0, n_rows, *, out=None
         out = torch.empty((n_rows, pitch), dtype=torch.float32, device=dev)
     role_id = layout.ROLE_ID[role] if isinstance(role, str) else int(role)
     check(_call("cev_ga_repopulate_f32", 
-        _h(dev), _ptr(elites), elites.shape[0], int(dim), pitch, sig, sig_dev,
+        _h(dev), _ptr(elites), elites.shape[0], int(dim), pitch, sig, sig_dev, float(crossover_rate),
         int(seed), role_id, int(gen), int(row0), int(n_rows), _ptr(out), _ptr(noise_out),
         _stream(dev)), "cev_ga_repopulate_f32")
     return out
@@ -423,6 +425,35 @@ def deepqn_forward(members, frames, c_in, n_actions):
                                     _ptr(frames), B, int(c_in), int(n_actions), _ptr(logits),
                                     _ptr(actions), _stream(dev)), "cev_deepqn_forward")
     return logits, actions
+
+
+def atari_synth_step(seed, ep0, ring, t, a_first=None, a_second=None, *, reward_out=None):
+    """Synthetic emulator step: frame ``t`` of every episode into slot t % 4 of ``ring`` (u8 [n, 4, 7056]);
+    returns the zero-sum reward r_first fp32[n] of the step (None for t = 0)."""
+    dev = _need_cuda(ring, a_first, a_second, reward_out)
+    n = ring.shape[0]
+    if ring.dtype != torch.uint8 or tuple(ring.shape[1:]) != (4, 7056):
+        raise _lib.CevError("atari_synth_step: ring must be uint8 [n, 4, 7056]")
+    if t > 0:
+        if a_first is None or a_second is None or a_first.dtype != torch.int32 or a_second.dtype != torch.int32:
+            raise _lib.CevError("atari_synth_step: int32 actions of both agents are needed for t >= 1")
+        if reward_out is None:
+            reward_out = torch.empty(n, dtype=torch.float32, device=dev)
+    check(_call("cev_atari_synth_step_u8", _h(dev), int(seed), int(ep0), n, int(t), _ptr(a_first), _ptr(a_second),
+                _ptr(ring), _ptr(reward_out), _stream(dev)), "cev_atari_synth_step_u8")
+    return reward_out
+
+
+def atari_observe(ring, t, seat, *, out=None):
+    """What agent ``seat`` (0 first_0, 1 second_0) observes after ``t`` emulator steps: u8 [n, 6, 84, 84]
+    (4 stacked frames, oldest first, + 2 agent-indicator planes)."""
+    dev = _need_cuda(ring, out)
+    n = ring.shape[0]
+    if out is None:
+        out = torch.empty((n, 6, 84, 84), dtype=torch.uint8, device=dev)
+    check(_call("cev_atari_observe_u8", _h(dev), _ptr(ring), n, int(t), int(seat), _ptr(out), _stream(dev)),
+          "cev_atari_observe_u8")
+    return out
 
 
 def fc_init(in_dim, seed, role, row0, n_rows, device, *, out=None):

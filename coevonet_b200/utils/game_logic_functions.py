@@ -44,12 +44,64 @@ def initialize_env(args):
     """Env factory (``utils/game_logic_functions.py:41-55``): returns the device
     env handle, seeded with the reference's constant 1870300."""
     if args.game != "simple_adversary_v3":
-        raise NotImplementedError(
-            f"{args.game}: the reference's Atari rollout is dead code (SURVEY.md Appendix C #9-11); "
-            "this build provides the DeepQN forward kernel (ops.deepqn_forward) only")
+        # no ROMs here and the reference's own Atari loop never runs (SURVEY.md Appendix C #9-11): the
+        # wrapper chain of utils/game_logic_functions.py:48-53 over the synthetic emulator (csrc/atari_synth.cu)
+        env = DeviceAtariEnv(args.game)
+        env.reset(seed=mpe_spec.ENV_SEED)
+        return env
     env = mpe_spec.DeviceMPEEnv(render_mode="human" if getattr(args, "render", False) else None)
     env.reset(seed=mpe_spec.ENV_SEED)
     return env
+
+
+class _Space:
+    def __init__(self, shape=None, n=None):
+        self.shape, self.n = shape, n
+
+
+class DeviceAtariEnv:
+    """Env handle of the synthetic Atari-like game: the attributes the reference reads from its wrapped
+    PettingZoo env (agents, observation_space(a).shape = (84, 84, 6), action_space(a).n = 6 for pong_v3 /
+    18 for boxing_v2) and the episode counter that keys the synthetic emulator."""
+
+    N_ACTIONS = {"pong_v3": 6, "boxing_v2": 18}
+
+    def __init__(self, game):
+        self.game = game
+        self.possible_agents = ["first_0", "second_0"]
+        self.agents = list(self.possible_agents)
+        self.seed_value = mpe_spec.ENV_SEED
+        self.episode = -1
+
+    def observation_space(self, agent):
+        return _Space(shape=(84, 84, 6))
+
+    def action_space(self, agent):
+        return _Space(n=self.N_ACTIONS[self.game])
+
+    def reset(self, seed=None, options=None):
+        if seed is not None:
+            self.seed_value, self.episode = int(seed), -1
+        self.episode += 1
+
+    def close(self):
+        pass
+
+
+def play_atari(env, player1, player2, args, eval=False):
+    """The reference's Atari episode loop (``utils/game_logic_functions.py:84-119``) with its three
+    defects repaired (argument count, ``forward`` signature, ``len(actions)``)
+    on the synthetic emulator: returns (rewards['first_0'], rewards['second_0'])."""
+    from ..atari_rollout import atari_rollout
+    dev = _device()
+    limit = args.max_evaluation_steps if eval else args.max_timesteps_per_episode
+    if limit is None:
+        raise ValueError("the synthetic Atari game never terminates: an agent-step limit is required")
+    n_act = env.action_space(env.agents[0]).n
+    r1, r2 = atari_rollout(0, player1.flat_row(dev).unsqueeze(0), player2.flat_row(dev), n_act, 1, limit,
+                           env.seed_value, ep0=env.episode,
+                           reference_compat=getattr(args, "reference_compat", True))
+    return float(r1), float(r2)
 
 
 def create_agent(env, args, role=None):
@@ -77,7 +129,7 @@ def play_game(env, player1, player2, adversary=None, args=None, eval=False):
     is False."""
     env.reset()
     if args.game != "simple_adversary_v3":
-        raise NotImplementedError("only simple_adversary_v3 has a rollout (Atari rollout is dead code upstream)")
+        return play_atari(env, player1, player2, args, eval)       # utils/game_logic_functions.py:224-227
     if adversary is None:
         raise ValueError("adversary not specified")
     dev = _device()

@@ -53,6 +53,7 @@ typedef void* cev_stream;               /* cudaStream_t */
 #define CEV_KIND_ENV 2
 #define CEV_KIND_FRAMES 3
 #define CEV_KIND_INIT 4
+#define CEV_KIND_XOVER 5
 
 int cev_version(void);
 const char* cev_last_error(void);
@@ -170,9 +171,16 @@ int cev_fc_forward_f32(cev_handle* h, const float* rows, int64_t pitch, int in_d
  * (local row r = global member row0 + r): global row 0 = elites[0]; global row
  * c >= 1 = elites[(c-1) % E] + sigma * N(0,1), Philox(seed, GA, role, gen,
  * member=c, param).  noise_out (optional) receives the N(0,1) draws.
+ *
+ * crossover_rate (extension, 0 = the reference: its README.md:47 promises crossover, its code has
+ * none): with this probability child c is first recombined -- every
+ * parameter from elites[(c-1) % E] or from a second, different elite, one Philox bit per parameter
+ * (Philox(seed, XOVER, role, gen, member=c): block 0xFFFFFFFF decides and picks the mate, block j4
+ * holds the mask bits of parameters 4*j4 .. 4*j4+3, bit set = first parent) -- and then mutated.
  */
 int cev_ga_repopulate_f32(cev_handle* h, const float* elites, int E,
                           int D, int64_t pitch, float sigma, const double* sigma_dev,
+                          float crossover_rate,
                           uint64_t seed, int role, uint32_t gen,
                           int64_t row0, int64_t n_rows,
                           float* out, float* noise_out, cev_stream stream);
@@ -307,6 +315,22 @@ int cev_generation_end_f64(cev_handle* h, const double* eval_out, int n_games, i
 int cev_deepqn_forward(cev_handle* h, const float* members, int P, int64_t pitch,
                        const uint8_t* frames, int B, int c_in, int n_actions,
                        float* logits, int32_t* actions, cev_stream stream);
+
+/*
+ * N4 -- synthetic Atari-like emulator around K2.  The reference's Atari rollout
+ * (utils/game_logic_functions.py:48-53,84-119) is dead code and needs ROMs; these two entry points give
+ * its wrapper chain a deterministic stand-in: cev_atari_synth_step_u8 writes frame `t` of episodes
+ * ep0 .. ep0+n-1 into slot t % 4 of a u8 ring [n, 4, 84*84] (Philox bytes keyed by episode, cycle and
+ * the joint action a_first + 32 a_second; t = 0 needs no actions) and the zero-sum reward
+ * r_first in [-1, 1) of that emulator step; cev_atari_observe_u8 builds what the agent `seat`
+ * (0 first_0, 1 second_0) observes after t steps: u8 [n, 6, 84*84] = frame_stack_v1(4) (oldest first,
+ * zeros before the first frames) + agent_indicator_v0 planes (255 on the agent's own plane).
+ */
+int cev_atari_synth_step_u8(cev_handle* h, uint64_t seed, int64_t ep0, int64_t n, int t,
+                            const int32_t* a_first, const int32_t* a_second, uint8_t* ring,
+                            float* r_first, cev_stream stream);
+int cev_atari_observe_u8(cev_handle* h, const uint8_t* ring, int64_t n, int t, int seat,
+                         uint8_t* obs, cev_stream stream);
 
 /*
  * Founder initialisation on the device.  Replaces create_agent -> MPEAgent -> FCNetwork

@@ -48,6 +48,41 @@ def ga_repopulate(pop, elite_idx, sigma, z):
     return out
 
 
+def ga_repopulate_crossover(elites, sigma, z, crossover_rate, seed, role_id, gen, members):
+    """Rows ``members`` (global ids) of the next population WITH the crossover extension (the
+    reference has none: README.md:47 vs genetic_algorithm.py:32-48).
+
+    child c >= 1: parent A = elites[(c-1) % E]; Philox(seed, XOVER, role, gen, member=c) block
+    0xFFFFFFFF: word0 < rate * 2^32 -> recombine with mate B = elites[((c-1) % E + 1 + word1 % (E-1)) % E];
+    block j4: bit 0 of word i set -> parameter 4*j4+i from A, else from B.  Then + sigma * z[c].
+    ``z`` fp32 [len(members), D]."""
+    from . import philox
+    elites = np.asarray(elites, dtype=np.float32)
+    E, D = elites.shape
+    out = np.empty((len(members), D), dtype=np.float32)
+    sig = np.float32(sigma)
+    thr = float(np.float32(crossover_rate)) * 4294967296.0
+    n4 = (D + 3) // 4
+    for r, c in enumerate(members):
+        c = int(c)
+        if c == 0:
+            out[r] = elites[0]
+            continue
+        a = (c - 1) % E
+        row = elites[a].copy()
+        if crossover_rate > 0 and E >= 2:
+            k0, k1 = philox.split_seed(seed)
+            tag = np.uint32((role_id & 0xFF) | (philox.KIND_XOVER << 8))
+            y = philox.philox4x32_10(np.uint32(0xFFFFFFFF), np.uint32(c), np.uint32(gen), tag, k0, k1)
+            if float(y[0]) < thr:
+                b = (a + 1 + int(y[1]) % (E - 1)) % E
+                w = philox.words(seed, philox.KIND_XOVER, role_id, gen, [c], n4).reshape(-1)[:D]
+                take_a = (w & np.uint32(1)).astype(bool)
+                row = np.where(take_a, elites[a], elites[b]).astype(np.float32)
+        out[r] = row + (sig * z[r, :D].astype(np.float32)).astype(np.float32)
+    return out
+
+
 def hof_update(hof, best_row):
     """FIFO Hall of Fame (genetic_algorithm.py:270-275): append newest, drop
     oldest; opponents are read newest-first ``hof[len-1-k]`` (:138-139)."""

@@ -31,6 +31,7 @@ KIND_GA = 1       # GA mutation noise     (agent.py:25-29 replacement)
 KIND_ENV = 2      # device-side initial env states (Appendix A.3 replacement)
 KIND_FRAMES = 3   # synthetic Atari frames
 KIND_INIT = 4     # device-side founder initialisation
+KIND_XOVER = 5    # GA crossover decisions / masks (extension; the reference has no crossover)
 
 ROLE_ID = {"agent_0": 0, "agent_1": 1, "adversary_0": 2}
 

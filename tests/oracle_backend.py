@@ -86,13 +86,20 @@ def gather_rows(src, idx, *, row0=0, n_local=None, out=None):
     return res
 
 
-def ga_repopulate(elites, dim, sigma, seed, role, gen, row0, n_rows, *, out=None, noise_out=None):
+def ga_repopulate(elites, dim, sigma, seed, role, gen, row0, n_rows, *, out=None, noise_out=None,
+                  crossover_rate=0.0):
     role_id = layout.ROLE_ID[role] if isinstance(role, str) else int(role)
     sigma = float(sigma)
     E, pitch = elites.shape
     res = torch.zeros((n_rows, pitch), dtype=torch.float32) if out is None else out
     el = elites.numpy()
     z = philox.normals(seed, philox.KIND_GA, role_id, gen, np.arange(row0, row0 + n_rows), dim)
+    if crossover_rate > 0:
+        rows = ga_es.ga_repopulate_crossover(el[:, :dim], sigma, z, crossover_rate, seed, role_id, gen,
+                                             np.arange(row0, row0 + n_rows))
+        res[:, :dim] = torch.from_numpy(rows)
+        res[:, dim:] = 0
+        return res
     for r in range(n_rows):
         c = row0 + r
         if c == 0:

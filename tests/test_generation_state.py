@@ -160,3 +160,29 @@ def test_resume_equals_uninterrupted_run_host_logic(tmp_path):
                 assert torch.equal(second.pop[r], full.pop[r]) and torch.equal(second.hof[r], full.hof[r])
         hs = second.host_state()
         assert hs["generations"] == 4 and len(hs["sigma_history"]["agent_1"]) == 5
+
+
+def test_crossover_restatement_properties():
+    """The crossover extension (the reference has none, README.md:47 vs genetic_algorithm.py:32-48):
+    rate 0 is the reference's clone + mutate; at rate 1 every child parameter comes from one of two
+    DIFFERENT elites, roughly half from each, and child 0 stays the unmutated best."""
+    from oracle import philox
+    rng = np.random.default_rng(2)
+    E, D, n = 3, 1000, 9
+    elites = rng.normal(size=(E, D)).astype(np.float32)
+    z = np.zeros((n, D), dtype=np.float32)
+    members = np.arange(n)
+    plain = ga_es.ga_repopulate_crossover(elites, 0.05, z, 0.0, 11, 1, 4, members)
+    for c in range(1, n):
+        assert np.array_equal(plain[c], elites[(c - 1) % E])
+    crossed = ga_es.ga_repopulate_crossover(elites, 0.05, z, 1.0, 11, 1, 4, members)
+    assert np.array_equal(crossed[0], elites[0])
+    for c in range(1, n):
+        a = (c - 1) % E
+        from_a = crossed[c] == elites[a]
+        others = [b for b in range(E) if b != a and np.array_equal(crossed[c][~from_a], elites[b][~from_a])]
+        assert len(others) == 1, "the complement must come from exactly one other elite"
+        assert 0.4 < from_a.mean() < 0.6
+    half = ga_es.ga_repopulate_crossover(elites, 0.05, np.zeros((400, D), dtype=np.float32), 0.5, 11, 1, 4, np.arange(400))
+    n_crossed = sum(not np.array_equal(half[c], elites[(c - 1) % E]) for c in range(1, 400))
+    assert 150 < n_crossed < 250

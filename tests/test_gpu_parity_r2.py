@@ -319,3 +319,85 @@ def test_resume_equals_uninterrupted_run(algorithm, tmp_path):
             assert torch.equal(second.hof[r], full.hof[r])
     hs = second.host_state()
     assert hs["generations"] == 2 * k and len(hs["rewards"]["agent_0"]) == 2 * k
+
+
+def test_crossover_kernel_matches_restatement():
+    """K3 with the crossover extension vs oracle/ga_es.ga_repopulate_crossover: parents, masks and the
+    mutated result bit for bit given the device noise; rate 0 equals the plain K3."""
+    from coevonet_b200 import layout, ops
+    from oracle import philox
+    in_dim, E, n, row0, seed, gen, sigma = 10, 4, 40, 3, 77, 5, 0.03
+    D, pitch = layout.fc_dim(in_dim), layout.fc_pitch(in_dim)
+    elites = _padded(weights.make_fc_rows(E, in_dim, 8, 0.02), in_dim)
+    noise = torch.empty((n, pitch), dtype=torch.float32, device="cuda")
+    for rate in (0.0, 0.35, 1.0):
+        got = ops.ga_repopulate(elites, D, sigma, seed, "agent_1", gen, row0, n, noise_out=noise,
+                                crossover_rate=rate).cpu().numpy()
+        z = noise.cpu().numpy()
+        want = ga_es.ga_repopulate_crossover(elites.cpu().numpy()[:, :D], sigma, z, rate, seed,
+                                             philox.ROLE_ID["agent_1"], gen, np.arange(row0, row0 + n))
+        assert np.array_equal(got[:, :D], want), f"rate {rate}"
+        assert np.all(got[:, D:] == 0)
+    plain = ops.ga_repopulate(elites, D, sigma, seed, "agent_1", gen, row0, n)
+    assert torch.equal(plain, ops.ga_repopulate(elites, D, sigma, seed, "agent_1", gen, row0, n, crossover_rate=0.0))
+
+
+# ---------------------------------------------------------------------------
+# N4: synthetic Atari-like rollout around K2
+# ---------------------------------------------------------------------------
+def test_synthetic_atari_emulator_matches_restatement():
+    from coevonet_b200 import ops
+    from oracle import atari_synth
+    n, seed, ep0 = 3, 1870300, 5
+    ring = torch.zeros((n, 4, 7056), dtype=torch.uint8, device="cuda")
+    ops.atari_synth_step(seed, ep0, ring, 0)
+    frames = [[atari_synth.frame(seed, ep0 + e, 0, 0)] for e in range(n)]
+    rng = np.random.default_rng(1)
+    for t in range(1, 7):
+        a1 = rng.integers(0, 18, n).astype(np.int32)
+        a2 = rng.integers(0, 18, n).astype(np.int32)
+        r = ops.atari_synth_step(seed, ep0, ring, t, torch.from_numpy(a1).cuda(), torch.from_numpy(a2).cuda())
+        for e in range(n):
+            j = int(a1[e]) + 32 * int(a2[e])
+            frames[e].append(atari_synth.frame(seed, ep0 + e, t, j))
+            assert float(r[e]) == float(atari_synth.reward_first(seed, ep0 + e, t, j))
+        for seat in (0, 1):
+            obs = ops.atari_observe(ring, t, seat).cpu().numpy()
+            for e in range(n):
+                assert np.array_equal(obs[e], atari_synth.observe(frames[e], seat)), (t, seat, e)
+
+
+@pytest.mark.parametrize("member_seat,limit", [(0, 6), (1, 5)])
+def test_synthetic_atari_rollout_matches_repaired_play_atari(member_seat, limit):
+    """P members x E episodes through the K2 forward vs the restated (repaired) play_atari loop."""
+    from coevonet_b200 import layout
+    from coevonet_b200.atari_rollout import atari_rollout
+    from oracle import atari_synth
+    n_act, P, E, seed = 6, 2, 2, 424242
+    rows = weights.make_dqn_rows(P + 1, 6, n_act, 17, bn_jitter=0.1)
+    pitch = layout.dqn_pitch(6, n_act)
+    dev_rows = torch.zeros((P + 1, pitch), device="cuda")
+    dev_rows[:, :rows.shape[1]] = torch.from_numpy(rows).cuda()
+    got1, got2 = atari_rollout(member_seat, dev_rows[:P].contiguous(), dev_rows[P], n_act, E, limit, seed)
+    for m in range(P):
+        for e in range(E):
+            first, second = (rows[m], rows[P]) if member_seat == 0 else (rows[P], rows[m])
+            (w1, w2), trace = atari_synth.play_atari(first, second, n_act, seed, m * E + e, limit, return_trace=True)
+            margins = [np.sort(lg)[-1] - np.sort(lg)[-2] for _, _, lg in trace]
+            if min(margins) > 1e-4:                  # an argmax decided at rounding level may fork the episode
+                assert abs(float(got1[m, e]) - w1) < 1e-9 and abs(float(got2[m, e]) - w2) < 1e-9, (m, e)
+
+
+def test_play_game_dispatches_to_the_atari_loop():
+    """The drop-in surface for --game pong_v3: initialize_env / create_agent / play_game(eval=...)."""
+    from coevonet_b200.utils.game_logic_functions import create_agent, initialize_env, play_game
+    args = types.SimpleNamespace(game="pong_v3", precision="float32", max_timesteps_per_episode=4,
+                                 max_evaluation_steps=6, reference_compat=True, render=False)
+    env = initialize_env(args)
+    assert env.agents == ["first_0", "second_0"] and env.observation_space("first_0").shape == (84, 84, 6)
+    torch.manual_seed(1)
+    a, b = create_agent(env, args), create_agent(env, args)
+    r = play_game(env, a.model, b.model, args=args)
+    r_eval = play_game(env, a.model, b.model, args=args, eval=True)
+    assert len(r) == 2 and len(r_eval) == 2 and all(np.isfinite(r)) and all(np.isfinite(r_eval))
+    assert -2.0 <= r[1] <= 2.0            # second_0's slot: first_0's rewards of 2 emulator steps in [-1, 1)
