@@ -1,4 +1,4 @@
-"""The committed bench lines (profiles/r01_bench_n*.json, written by bench.py on a B200) carry every key
+"""The committed bench lines (profiles/r0*_bench_n*.json, written by bench.py on a B200) carry every key
 the measurement contract names; bench.py's CLI parses the driver's flags.  No GPU needed."""
 import json
 import os
@@ -49,3 +49,35 @@ def test_bench_cli_accepts_the_driver_flags():
     assert out.returncode == 0
     for flag in ("--gpus", "--steps", "--warmup", "--impl"):
         assert flag in out.stdout
+
+
+def test_round2_line_carries_parity_secondary_and_floors():
+    d = _line("r02_bench_n1.json")
+    p = d["parity"]
+    assert p["members_sampled"] >= 3 * 128 and 0.0 <= p["member_match_frac"] <= 1.0 and p["episode_forks"] >= 0
+    fl = d["roofline"]["floors"]
+    assert fl["per_launch_hbm_us"] > fl["per_launch_fp32_us"] > 0           # `bound` hbm is the binding floor
+    assert abs(fl["per_rollout_hbm_bytes_streamed"] - 25 * fl["per_rollout_hbm_bytes_if_rows_stayed_on_chip"]) < 1
+    assert d["roofline"]["fp32_peak_theoretical_tflops"] >= d["roofline"]["fp32_peak_tflops"] * 0.95
+    assert d["e2e"]["steps"] == d["steps"]                                 # e2e over the full --steps, host clock
+    s = d["secondary"]
+    names = " ".join(k["kernel"] for k in s["kernels"])
+    for k in ("K3", "K5", "K6", "K7"):
+        assert k in names
+    for k in s["kernels"]:
+        assert k["us_per_launch"] > 0 and k["rows"] in (1024, 8192)
+        if k["bound"] != "alu":
+            assert abs(k["frac"] - k["achieved"] / k["peak"]) < 1e-9
+    assert s["config3_ga"]["members_per_gpu"] == 8192 and s["config3_ga"]["ms_per_generation"] > 0
+    assert [c["frames_per_member"] for c in s["config4_dqn_forward"]] == [1, 4]
+    assert s["config5_dqn_es"]["population"] == 4096
+
+
+def test_round2_multi_gpu_lines_check_the_sharded_run_against_one_gpu():
+    d1 = _line("r02_bench_n1.json")
+    for n in (2, 8):
+        d = _line(f"r02_bench_n{n}.json")
+        assert d["n_gpus"] == n and d["sharded_equals_single"] is True
+        assert d["sharded_check"]["rewards_bit_identical"] is True
+        assert 0.9 * n < d["value"] / d1["value"] < 1.1 * n
+        assert d["secondary"]["config3_ga"]["population"] == 8192 * n
