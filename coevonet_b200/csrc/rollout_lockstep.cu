@@ -59,11 +59,12 @@ struct LsBuffers {
     float* gap;        // [3][N]
     float* w2split;    // [2 seats][K][hi, lo][256][512]
     double* l1stats;   // [2 seats][K][132]
+    double* ml1stats;  // [P][132]  the members' own layer-1 statistics (tensor-core member form)
 };
 
 static size_t ls_align(size_t x) { return (x + 255) & ~(size_t)255; }
 
-static size_t ls_carve(void* base, int64_t N, int K, LsBuffers* b) {
+static size_t ls_carve(void* base, int64_t N, int K, int P, LsBuffers* b) {
     size_t off = 0;
     char* p = static_cast<char*>(base);
     auto take = [&](size_t bytes) {
@@ -81,6 +82,7 @@ static size_t ls_carve(void* base, int64_t N, int K, LsBuffers* b) {
     t.act = static_cast<int32_t*>(take((size_t)3 * N * sizeof(int32_t)));
     t.gap = static_cast<float*>(take((size_t)3 * N * sizeof(float)));
     t.l1stats = static_cast<double*>(take((size_t)2 * K * LS_L1S * sizeof(double)));
+    t.ml1stats = static_cast<double*>(take((size_t)P * LS_L1S * sizeof(double)));
     if (b) *b = t;
     return off;
 }
@@ -243,10 +245,8 @@ __global__ void __launch_bounds__(256) ls_split_w2_kernel(const LsPrepParams p) 
 // wbar[j] = mean over the 512 rows of column j of [W1 | b1]; C[a][b] = row covariance (biased).
 // LayerNorm-1 of y = W1 x + b1:  mean(y) = wbar . z,  var(y) = z^T C z  with z = [x; 1]
 // (MPE/fcnetwork.py:44: nn.LayerNorm(512), biased variance).
-__global__ void __launch_bounds__(512) ls_l1stats_kernel(const LsPrepParams p) {
-    const int oi = blockIdx.x / p.K, k = blockIdx.x % p.K;
-    const int in = seat_in_dim(p.seat[oi]), d = in + 1;
-    const float* row = p.opp[oi] + (int64_t)k * p.opp_pitch[oi];
+__device__ __forceinline__ void ls_l1stats_row(const float* __restrict__ row, int in, double* __restrict__ out) {
+    const int d = in + 1;
     const float* w1 = row;
     const float* b1 = row + H1 * in;
     __shared__ float cols[11][H1];          // [W1 | b1] transposed: column a of all 512 rows
@@ -264,7 +264,6 @@ __global__ void __launch_bounds__(512) ls_l1stats_kernel(const LsPrepParams p) {
         if (lane == 0) wbar[a] = s / H1;
     }
     __syncthreads();
-    double* out = p.l1stats + (size_t)blockIdx.x * LS_L1S;
     if (t < 11) out[t] = wbar[t];
     for (int pr = warp; pr < 121; pr += 16) {
         const int a = pr / 11, b = pr % 11;
@@ -279,9 +278,30 @@ __global__ void __launch_bounds__(512) ls_l1stats_kernel(const LsPrepParams p) {
     }
 }
 
+__global__ void __launch_bounds__(512) ls_l1stats_kernel(const LsPrepParams p) {
+    const int oi = blockIdx.x / p.K, k = blockIdx.x % p.K;
+    ls_l1stats_row(p.opp[oi] + (int64_t)k * p.opp_pitch[oi], seat_in_dim(p.seat[oi]),
+                   p.l1stats + (size_t)blockIdx.x * LS_L1S);
+}
+
+// the same statistics for every member row (tensor-core member form), once per rollout
+__global__ void __launch_bounds__(512) ls_member_l1stats_kernel(const float* __restrict__ members, int64_t pitch, int in,
+                                                                double* __restrict__ out) {
+    ls_l1stats_row(members + (int64_t)blockIdx.x * pitch, in, out + (size_t)blockIdx.x * LS_L1S);
+}
+
 // ---------------------------------------------------------------------------------------------
 // member forward (FP32 pipe)
 // ---------------------------------------------------------------------------------------------
+#ifndef LS_MEMBER_TC_DEFAULT
+#define LS_MEMBER_TC_DEFAULT 0
+#endif
+#ifndef LS_GRID_OPP_DEFAULT
+#define LS_GRID_OPP_DEFAULT 0                     // 0 = one CTA per SM
+#endif
+#ifndef LS_GRID_MEM_DEFAULT
+#define LS_GRID_MEM_DEFAULT 0
+#endif
 constexpr int LS_BT = 16;                         // episodes per CTA
 constexpr int LS_MT = 128;                        // threads per member CTA (4 warps)
 constexpr int LS_MW = LS_MT / 32;
@@ -1064,11 +1084,16 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
+}  // namespace cev
+
+#include "ls_member_tc.cuh"
+
+namespace cev {
 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-int rollout_lockstep_launches(int n_cycles) { return 3 + 3 * n_cycles; }
+int rollout_lockstep_launches(int n_cycles) { return 4 + 3 * n_cycles; }
 
 int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t stream) {
     if (p.P <= 0 || p.K <= 0 || p.E <= 0) return CEV_OK;
@@ -1078,7 +1103,7 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
         return CEV_ERR_UNSUPPORTED;
     }
     const int64_t N = (int64_t)p.P * p.K * p.E;
-    const size_t need = ls_carve(nullptr, N, p.K, nullptr);
+    const size_t need = ls_carve(nullptr, N, p.K, p.P, nullptr);
     if (h->ls_workspace_bytes < need) {
         if (h->ls_workspace) CEV_CUDA(cudaFree(h->ls_workspace));
         h->ls_workspace = nullptr;
@@ -1087,7 +1112,7 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
         h->ls_workspace_bytes = need;
     }
     LsBuffers b;
-    ls_carve(h->ls_workspace, N, p.K, &b);
+    ls_carve(h->ls_workspace, N, p.K, p.P, &b);
     const int ms = p.member_seat;
     const int seat_of[2] = {ms == 0 ? 1 : 0, ms == 2 ? 1 : 2};
 
@@ -1097,6 +1122,8 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
                                       (int)LsMemberSmem::total));
         CEV_CUDA(cudaFuncSetAttribute(ls_member_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CEV_CUDA(cudaFuncSetAttribute(ls_opp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OP_SMEM));
+        CEV_CUDA(cudaFuncSetAttribute(ls_member_tc_kernel<IN_ADV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MT_SMEM));
+        CEV_CUDA(cudaFuncSetAttribute(ls_member_tc_kernel<IN_GOOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MT_SMEM));
         configured[h->device] = true;
     }
 
@@ -1113,8 +1140,27 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
     ls_split_w2_kernel<<<dim3(32, 2 * p.K), 256, 0, stream>>>(pp);
     ls_l1stats_kernel<<<2 * p.K, 512, 0, stream>>>(pp);
 
+    // ---- member form: 1 = tensor cores, persistent, beside the opponent kernel (ls_member_tc.cuh); 0 = FP32 pipe ----
+    static const int member_tc = getenv("CEV_LS_MEMBER_TC") ? atoi(getenv("CEV_LS_MEMBER_TC")) : LS_MEMBER_TC_DEFAULT;
+    if (member_tc)
+        ls_member_l1stats_kernel<<<p.P, 512, 0, stream>>>(p.members, p.member_pitch, seat_in_dim(ms), b.ml1stats);
+
     // ---- tensor maps ---------------------------------------------------------------------------
-    CUtensorMap map_w2, map_b;
+    CUtensorMap map_w2, map_b, map_wtc;
+    if (member_tc) {
+        const FcOffsets om = fc_offsets(seat_in_dim(ms));
+        cuuint64_t dims[3] = {(cuuint64_t)H1, (cuuint64_t)H2, (cuuint64_t)p.P};
+        cuuint64_t strides[2] = {(cuuint64_t)H1 * 4, (cuuint64_t)p.member_pitch * 4};
+        cuuint32_t box[3] = {MT_BK, H2, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = encode(&map_wtc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.members + om.fc2w), dims,
+                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("rollout_lockstep: cuTensorMapEncodeTiled(member fc2, tensor-core form) failed with %d", (int)r);
+            return CEV_ERR_CUDA;
+        }
+    }
     {
         const FcOffsets om = fc_offsets(seat_in_dim(ms));
         cuuint64_t dims[3] = {(cuuint64_t)H1, (cuuint64_t)H2, (cuuint64_t)p.P};
@@ -1192,6 +1238,30 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
     op.status = p.status;
     int opp_grid = op.n_jobs < h->n_sm ? op.n_jobs : h->n_sm;
 
+    LsMemberTcParams tp{};
+    tp.members = p.members;
+    tp.pitch = p.member_pitch;
+    tp.KE = mp.KE;
+    tp.n_chunks = mp.n_chunks;
+    tp.seat = ms;
+    tp.n_jobs = (int)member_ctas;
+    tp.N = N;
+    tp.obs = mp.obs;
+    tp.act = mp.act;
+    tp.gap = mp.gap;
+    tp.l1stats = b.ml1stats;
+    tp.status = p.status;
+    int mem_grid = tp.n_jobs < h->n_sm ? tp.n_jobs : h->n_sm;
+    if (member_tc) {
+        // The SMs are shared out between the two persistent kernels: the member kernel is bound by the HBM stream
+        // and keeps its rate on about half of the SMs, the opponent kernel is bound by the tensor pipe of the SMs
+        // it gets.  CEV_LS_GRID_OPP / CEV_LS_GRID_MEM override the split (development aid).
+        static const int g_opp = getenv("CEV_LS_GRID_OPP") ? atoi(getenv("CEV_LS_GRID_OPP")) : LS_GRID_OPP_DEFAULT;
+        static const int g_mem = getenv("CEV_LS_GRID_MEM") ? atoi(getenv("CEV_LS_GRID_MEM")) : LS_GRID_MEM_DEFAULT;
+        if (g_opp > 0 && g_opp < opp_grid) opp_grid = g_opp;
+        if (g_mem > 0 && g_mem < mem_grid) mem_grid = g_mem;
+    }
+
     // development aids: CEV_LS_SKIP bit 0 = no opponent kernel, bit 1 = no member kernel (timing only,
     // results are then invalid); CEV_LS_FORK=1 = opponent kernel on a side stream beside the member kernel
     static const int skip = getenv("CEV_LS_SKIP") ? atoi(getenv("CEV_LS_SKIP")) : 0;
@@ -1204,7 +1274,7 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
                                       (int)LsMemberSmem::total + member_pad));
         pad_configured = true;
     }
-    static const int want_fork = getenv("CEV_LS_FORK") ? atoi(getenv("CEV_LS_FORK")) : 0;
+    static const int want_fork = getenv("CEV_LS_FORK") ? atoi(getenv("CEV_LS_FORK")) : (member_tc ? 1 : 0);
     // The two forwards of a world step are independent (same observations), use different pipes
     // (tensor vs FP32/HBM) and both end in a partial wave, so running them on two streams lets the
     // block scheduler fill one kernel's tail with the other's CTAs.  Measured: +4 % at 1024 members,
@@ -1221,6 +1291,7 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
         if (p.trace_logits) {
             op.logits = p.trace_logits + (size_t)c * 3 * N * NACT;
             mp.logits = op.logits + (size_t)ms * N * NACT;
+            tp.logits = mp.logits;
         }
         ep.forced = p.trace_forced ? p.trace_forced + (size_t)c * 3 * N : nullptr;
         ep.act_out = p.trace_actions ? p.trace_actions + (size_t)c * 3 * N : nullptr;
@@ -1245,7 +1316,12 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
         }
         if (!(skip & 2)) {
             tick(0, 0);
-            ls_member_kernel<<<(unsigned)member_ctas, LS_MT, LsMemberSmem::total + member_pad, stream>>>(map_w2, mp);
+            if (member_tc) {
+                if (ms == 0) ls_member_tc_kernel<IN_ADV><<<mem_grid, MT_THREADS, MT_SMEM, stream>>>(map_wtc, tp);
+                else ls_member_tc_kernel<IN_GOOD><<<mem_grid, MT_THREADS, MT_SMEM, stream>>>(map_wtc, tp);
+            } else {
+                ls_member_kernel<<<(unsigned)member_ctas, LS_MT, LsMemberSmem::total + member_pad, stream>>>(map_w2, mp);
+            }
             tick(0, 1);
         }
         if (fork && !(skip & 1)) CEV_CUDA(cudaStreamWaitEvent(stream, h->join_ev, 0));

@@ -112,7 +112,7 @@ int main(int argc, char** argv) {
         }
         const size_t smem = (size_t)c.slots * c.chunk + 1024;
         CK(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        for (int grid : {148, 296}) {
+        for (int grid : {37, 74, 111, 148, 296}) {
             if (grid == 296 && smem > 110 * 1024) continue;
             float best = 1e9f;
             for (int rep = 0; rep < 4; ++rep) {
