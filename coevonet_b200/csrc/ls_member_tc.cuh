@@ -2,26 +2,32 @@
 //
 // The member's own forward (FCNetwork.forward, MPE/fcnetwork.py:37-70, with the member's OWN weights:
 // evolutionary_strategy.py:63-116 mutate_weights, genetic_algorithm.py:125-217) is, per member and world step,
-// H[256, 16 episodes] = W2_m[256, 512] . h1[16, 512]^T with 512 KB of W2_m that nobody else reads: the stage is
-// bound by the HBM stream of the member rows, and a CTA that only streams does not need the FP32 pipe of its SM.
-// This form therefore keeps the FMA pipe out of it (3xTF32 on tcgen05, the structure of the K2 fc stage,
-// deepqn_tc.cu) and runs as a PERSISTENT kernel on a subset of the SMs, so that the opponent kernel
-// (tensor-pipe bound, ls_opp_kernel) runs beside it on the other SMs instead of after it.
+// H[256, 16 episodes] = W2_m[256, 512] . h1[16, 512]^T with 512 KB of W2_m that nobody else reads: the stage streams
+// the member rows from HBM once per world step.  This form keeps the FMA pipe out of it (3xTF32 on tcgen05) and runs
+// as a PERSISTENT kernel on a share of the SMs, so that the opponent kernel (tensor-pipe bound, ls_opp_kernel) runs
+// beside it on the other SMs instead of after it.
 //
 // One CTA per SM, job = (member, block of 16 episodes).  Per k-tile of 32:
 //   warp 0      TMA: the raw W2 tile [256 rows x 32 k] (3-D tensor map (k, row, member), 128B swizzle, 256B L2
 //               promotion) into a 5-slot ring, with the k-tile's 32 rows of the member's layer 1 (fc1.W | fc1.b |
-//               ln1.g | ln1.b, 1.7 KB) behind it; per job the tail block (fc2.b | ln2.g | ln2.b | out.W | out.b)
-//   warps 2-9   W2 lo = w - trunc_tf32(w) -> TENSOR MEMORY (tcgen05.st; the MMA takes it as a TMEM A operand), and
-//               the activations of this k-tile: relu(LN1(W1 x + b1)) for the 16 episodes, split into hi | lo and
-//               stored K-major behind the W2 tile, so [x_hi | x_lo] is ONE 32-row N operand.  LayerNorm-1 uses
-//               the closed-form row statistics (mean = wbar . z, var = z^T C z, fp64; ls_l1stats_kernel over
-//               the member rows, once per rollout), so a k-tile never needs the whole 512-vector
-//   warps 1,14  16 x tcgen05.mma.cta_group::1.kind::tf32 per k-tile (2 row tiles, one per issuing warp, x 4 k-steps x
-//               {w_hi . [x_hi | x_lo] (N = 32), w_lo (TMEM) . x_hi (N = 16)}) into ping-pong accumulators
-//   warps 10-13 epilogue: tcgen05.ld, + fc2.b into shared memory, LayerNorm-2 + ReLU + output layer + first-max
-//               argmax (MPE/fcnetwork.py:53-90); then the observations and LayerNorm-1 statistics of the job
-//               after the next one, which the producers pick up from shared memory
+//               ln1.g | ln1.b, 1.7 KB) beside it; per job the tail block (fc2.b | ln2.g | ln2.b | out.W | out.b)
+//   warps 2-9   two groups of four warps take alternate k-tiles: read the W2 tile ONCE from shared memory and write
+//               both MMA A operands to TENSOR MEMORY (tcgen05.st, lane = W2 row): hi = the raw fp32 word (the tensor
+//               core reads it truncated to TF32) and lo = w - trunc_tf32(w).  The raw slot is free again as soon as
+//               it has been read (not when its MMAs retire), and the MMAs fetch nothing but the small activation
+//               tile from shared memory: with W2 as a shared-memory operand the stage moved 115 KB per k-tile
+//               through the 128 B/clk shared-memory port (TMA fill 34 + LDS 34 + operand fetch 44) and was bound by
+//               it at ~1050 cycles per k-tile.  The same warps compute the activations of the k-tile,
+//               relu(LN1(W1 x + b1)) for the 16 episodes, split into hi | lo and stored K-major as ONE 32-row N
+//               operand [x_hi | x_lo].  LayerNorm-1 uses the closed-form row statistics (mean = wbar . z,
+//               var = z^T C z, fp64; ls_member_l1stats_kernel, once per rollout)
+//   warps 1,14  16 x tcgen05.mma.cta_group::1.kind::tf32 per k-tile, A from tensor memory (2 row tiles, one per
+//               issuing warp, x 4 k-steps x {w_hi, w_lo} . [x_hi | x_lo], N = 32) into ping-pong accumulators; a
+//               tcgen05.mma of this size occupies the tensor pipe ~45 cycles whatever N <= 64 is
+//               (scripts/probe/mma_probe.cu), so 720 cycles per k-tile is the floor of this form
+//   warps 10-13 epilogue: tcgen05.ld, (x_hi columns + x_lo columns) + fc2.b into shared memory, LayerNorm-2 + ReLU +
+//               output layer + first-max argmax (MPE/fcnetwork.py:53-90); then the observations and LayerNorm-1
+//               statistics of the job after the next one, which the producers pick up from shared memory
 #pragma once
 
 namespace cev {
@@ -29,63 +35,61 @@ namespace cev {
 constexpr int MT_THREADS = 480;                               // warp 0 TMA, 1 + 14 MMA, 2-9 producers, 10-13 epilogue
 constexpr int MT_PROD_WARPS = 8;
 constexpr int MT_BK = 32, MT_KT = H1 / MT_BK;                 // 16 k-tiles of 128 bytes
-constexpr int MT_NB = LS_BT;                                  // 16 episodes = MMA N
-constexpr int MT_R = 5, MT_L = 4;                             // raw slots (shared memory), W2-lo slots (tensor memory)
+constexpr int MT_NB = LS_BT;                                  // 16 episodes
+constexpr int MT_R = 5, MT_L = 3;                             // raw slots (shared memory), operand slots (tensor memory)
 constexpr uint32_t MT_A_BYTES = H2 * MT_BK * 4;               // 32 KB
 constexpr uint32_t MT_X_BYTES = MT_NB * MT_BK * 4;            // 2 KB
-constexpr uint32_t MT_SLOT = MT_A_BYTES + 2 * MT_X_BYTES;     // W2 raw | x hi | x lo = 36 KB
+constexpr uint32_t MT_XSLOT = 2 * MT_X_BYTES;                 // x hi | x lo = 4 KB, one per operand slot
 constexpr uint32_t MT_W1C_FLOATS = MT_BK * IN_GOOD + 3 * MT_BK;   // layer-1 chunk of a k-tile: fc1.W rows | fc1.b | ln1.g | ln1.b
 constexpr uint32_t MT_W1C_BYTES = MT_W1C_FLOATS * 4;          // 1,664
 constexpr uint32_t MT_TAIL_BYTES = LS_TAIL_FLOATS * 4;        // 8,224
-constexpr size_t MT_OFF_W1C = (size_t)MT_R * MT_SLOT;         // [R] layer-1 chunks, one per raw slot
-constexpr size_t MT_OFF_HS = MT_OFF_W1C + (size_t)MT_R * MT_W1C_BYTES;   // [256 rows][16 episodes] fp32
+constexpr size_t MT_OFF_X = (size_t)MT_R * MT_A_BYTES;        // [L] activation tiles
+constexpr size_t MT_OFF_W1C = MT_OFF_X + (size_t)MT_L * MT_XSLOT;         // [R] layer-1 chunks, one per raw slot
+constexpr size_t MT_OFF_HS = MT_OFF_W1C + (size_t)MT_R * MT_W1C_BYTES;    // [256 rows][16 episodes] fp32
 constexpr size_t MT_OFF_TAIL = MT_OFF_HS + (size_t)H2 * MT_NB * 4;
 constexpr size_t MT_OFF_OBS = MT_OFF_TAIL + MT_TAIL_BYTES;    // [2][16][12] fp32
 constexpr size_t MT_OFF_STAT = MT_OFF_OBS + 2 * MT_NB * LS_OBS_PAD * 4;   // [2][16] (mean, rstd)
 constexpr size_t MT_OFF_RED = MT_OFF_STAT + 2 * MT_NB * 8;    // redA [4][16] | redB [4][16] | redC [4][5][16]
 constexpr size_t MT_OFF_BAR = MT_OFF_RED + (size_t)(2 + NACT) * 4 * MT_NB * 4;
 constexpr size_t MT_SMEM = MT_OFF_BAR + 256 + 1024 /*alignment*/;
-constexpr int MT_ACC = 3 * MT_NB;                             // accumulator columns per row tile: hh | hl | lh
-constexpr int MT_TM_LO = 2 * 2 * MT_ACC;                      // first TMEM column of the W2-lo slots
-constexpr int MT_TM_LSLOT = 2 * MT_BK;                        // columns per lo slot: 2 row tiles x 32 k
-static_assert(MT_TM_LO + MT_L * MT_TM_LSLOT <= 512, "tensor memory budget");
-static_assert(MT_SLOT % 1024 == 0, "slots must keep the 1024-byte alignment of the swizzle atoms");
+constexpr int MT_ACC = 2 * MT_NB;                             // accumulator columns per row tile: . x_hi | . x_lo
+constexpr int MT_TM_OP = 2 * 2 * MT_ACC;                      // first TMEM column of the operand slots (after 2 x 2 accumulators)
+constexpr int MT_TM_SLOT = 2 * 2 * MT_BK;                     // columns per operand slot: 2 row tiles x (hi 32 | lo 32)
+static_assert(MT_TM_OP + MT_L * MT_TM_SLOT <= 512, "tensor memory budget");
+static_assert(MT_OFF_X % 1024 == 0 && MT_XSLOT % 1024 == 0, "operand tiles must keep the 1024-byte alignment of the swizzle atoms");
 static_assert(MT_OFF_W1C % 16 == 0 && MT_W1C_BYTES % 16 == 0 && MT_OFF_TAIL % 16 == 0 && MT_OFF_BAR % 8 == 0,
               "bulk-copy alignment");
 static_assert(MT_SMEM <= 232448, "member stage exceeds the 227 KB shared-memory limit");
 constexpr uint32_t MT_IDESC32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * MT_NB) >> 3) << 17) |
                                 ((uint32_t)(128 >> 4) << 24);
-constexpr uint32_t MT_IDESC16 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(MT_NB >> 3) << 17) |
-                                ((uint32_t)(128 >> 4) << 24);
 
-// The eight MMAs of one row tile and k-tile (4 k-steps x {w_hi . [x_hi | x_lo] (N = 32), w_lo (TMEM) . x_hi (N = 16)})
-// plus the two commits that release the raw slot and the lo slot, issued by one elected lane of a converged warp.
-__device__ __forceinline__ void mt_issue_ktile(uint32_t d_tmem, uint64_t w_hi, uint64_t x_hilo, uint32_t lo_tmem,
-                                               uint32_t accumulate, uint32_t bar_raw, uint32_t bar_lo) {
+// The eight MMAs of one row tile and k-tile (4 k-steps x {w_hi, w_lo} (tensor memory) . [x_hi | x_lo] (N = 32)) plus the
+// commit that releases the operand slot, issued by one elected lane of a CONVERGED warp: inside a divergent
+// `if (lane == 0)` every tcgen05.mma costs an ELECT + R2UR.BROADCAST chain (~20 instructions).
+__device__ __forceinline__ void mt_issue_ktile(uint32_t d_tmem, uint32_t a_tmem, uint64_t x_hilo, uint32_t accumulate,
+                                               uint32_t bar_op) {
     asm volatile(
         "{\n"
         ".reg .pred pe, pa, pt;\n"
-        ".reg .b64 a1, a2, a3, b1, b2, b3;\n"
-        ".reg .b32 l1, l2, l3, dl;\n"
+        ".reg .b64 b1, b2, b3;\n"
+        ".reg .b32 h1, h2, h3, l0, l1, l2, l3;\n"
         "elect.sync _|pe, 0xffffffff;\n"
-        "setp.ne.b32 pa, %4, 0;\n"
+        "setp.ne.b32 pa, %3, 0;\n"
         "setp.eq.b32 pt, 0, 0;\n"
-        "add.s64 a1, %1, 2;\n add.s64 a2, %1, 4;\n add.s64 a3, %1, 6;\n"
         "add.s64 b1, %2, 2;\n add.s64 b2, %2, 4;\n add.s64 b3, %2, 6;\n"
-        "add.u32 l1, %3, 8;\n add.u32 l2, %3, 16;\n add.u32 l3, %3, 24;\n"
-        "add.u32 dl, %0, 32;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %7, pa;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [dl], [%3], %2, %8, pa;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], a1, b1, %7, pt;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [dl], [l1], b1, %8, pt;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], a2, b2, %7, pt;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [dl], [l2], b2, %8, pt;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], a3, b3, %7, pt;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [dl], [l3], b3, %8, pt;\n"
-        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n"
-        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n"
+        "add.u32 h1, %1, 8;\n add.u32 h2, %1, 16;\n add.u32 h3, %1, 24;\n"
+        "add.u32 l0, %1, 32;\n add.u32 l1, %1, 40;\n add.u32 l2, %1, 48;\n add.u32 l3, %1, 56;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [l0], %2, %5, pa;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %5, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [l1], b1, %5, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [h1], b1, %5, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [l2], b2, %5, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [h2], b2, %5, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [l3], b3, %5, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [h3], b3, %5, pt;\n"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%4];\n"
         "}\n" ::"r"(d_tmem),
-        "l"(w_hi), "l"(x_hilo), "r"(lo_tmem), "r"(accumulate), "r"(bar_raw), "r"(bar_lo), "r"(MT_IDESC32), "r"(MT_IDESC16)
+        "r"(a_tmem), "l"(x_hilo), "r"(accumulate), "r"(bar_op), "r"(MT_IDESC32)
         : "memory");
 }
 __device__ __forceinline__ void mt_commit_elected(uint32_t bar) {
@@ -113,7 +117,8 @@ __global__ void __launch_bounds__(MT_THREADS, 1)
 ls_member_tc_kernel(const __grid_constant__ CUtensorMap map_w, const LsMemberTcParams p) {
     extern __shared__ unsigned char mt_raw[];
     unsigned char* base = mt_raw + ((1024u - (tc_smem_u32(mt_raw) & 1023u)) & 1023u);
-    unsigned char* raw_mem = base;                                    // R x (W2 raw | x hi | x lo)
+    unsigned char* raw_mem = base;                                    // [R] raw W2 tiles
+    unsigned char* x_mem = base + MT_OFF_X;                           // [L] (x hi | x lo)
     float* hs = reinterpret_cast<float*>(base + MT_OFF_HS);
     unsigned char* w1c_mem = base + MT_OFF_W1C;                       // [R][fc1.W rows of the k-tile | fc1.b | ln1.g | ln1.b]
     float* tail = reinterpret_cast<float*>(base + MT_OFF_TAIL);
@@ -143,7 +148,7 @@ ls_member_tc_kernel(const __grid_constant__ CUtensorMap map_w, const LsMemberTcP
         *flag = 0;
         for (int i = 0; i < MT_R; ++i) {
             tc_mbar_init(bar_raw_full + i, 1);
-            tc_mbar_init(bar_raw_empty + i, 2);        // one commit per MMA warp
+            tc_mbar_init(bar_raw_empty + i, MT_PROD_WARPS / 2);    // read by the producer warps of the k-tile's group
         }
         for (int i = 0; i < MT_L; ++i) {
             tc_mbar_init(bar_lo_full + i, MT_PROD_WARPS / 2);      // one arrive per producer warp of the k-tile's group
@@ -159,7 +164,7 @@ ls_member_tc_kernel(const __grid_constant__ CUtensorMap map_w, const LsMemberTcP
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 1) {
-        // 2 (ping-pong) x 2 (row tiles) x 48 accumulator columns = 192, then 4 W2-lo slots x 64 columns -> 448 of 512
+        // 2 (ping-pong) x 2 (row tiles) x 32 accumulator columns = 128, then 3 operand slots x 128 columns -> 512
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tc_smem_u32(tmem_slot)),
                      "r"(512u)
                      : "memory");
@@ -181,7 +186,7 @@ ls_member_tc_kernel(const __grid_constant__ CUtensorMap map_w, const LsMemberTcP
                     const uint32_t rs = it % MT_R, use = it / MT_R;
                     if (use > 0) tc_mbar_wait(bar_raw_empty + rs, (use - 1) & 1);
                     tc_mbar_expect_tx(bar_raw_full + rs, MT_A_BYTES + W1ROWS_BYTES + 3 * MT_BK * 4);
-                    tma_load_3d(raw_mem + (size_t)rs * MT_SLOT, &map_w, bar_raw_full + rs, kt * MT_BK, 0, m);
+                    tma_load_3d(raw_mem + (size_t)rs * MT_A_BYTES, &map_w, bar_raw_full + rs, kt * MT_BK, 0, m);
                     float* c = reinterpret_cast<float*>(w1c_mem + (size_t)rs * MT_W1C_BYTES);
                     bulk_g2s(c, mrow + kt * MT_BK * IN, W1ROWS_BYTES, bar_raw_full + rs);
                     bulk_g2s(c + MT_BK * IN, mrow + om.fc1b + kt * MT_BK, MT_BK * 4, bar_raw_full + rs);
@@ -195,11 +200,8 @@ ls_member_tc_kernel(const __grid_constant__ CUtensorMap map_w, const LsMemberTcP
         }
     } else if (warp == 1 || warp == 14) {
         // ===================== MMA issuers: warp 1 = W2 rows 0..127, warp 14 = rows 128..255 =====================
-        // A tcgen05.mma of this size costs ~45 cycles of the tensor pipe whatever N <= 64 is (measured,
-        // scripts/probe/mma_probe.cu) plus ~60 issue-side instructions, so the 16 instructions of a k-tile are
-        // shared out between two issuing threads; every operand is computed warp-uniformly outside the elected branch.
         const int t = warp == 1 ? 0 : 1;
-        const uint32_t raw_base = tc_smem_u32(raw_mem);
+        const uint32_t x_base = tc_smem_u32(x_mem);
         uint32_t it = 0, js = 0;
         for (int job = job0; job < p.n_jobs; job += job_stride, ++js) {
             const uint32_t as = js & 1, ause = js >> 1;
@@ -207,18 +209,12 @@ ls_member_tc_kernel(const __grid_constant__ CUtensorMap map_w, const LsMemberTcP
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             const uint32_t d_tmem = tmem_base + as * (2 * MT_ACC) + t * MT_ACC;
             for (int kt = 0; kt < MT_KT; ++kt, ++it) {
-                const uint32_t rs = it % MT_R, ruse = it / MT_R, ls = it % MT_L, luse = it / MT_L;
-                const uint32_t hi_addr = raw_base + rs * MT_SLOT;
-                const uint64_t w_hi = umma_desc_sw128(hi_addr + t * (128 * MT_BK * 4));
-                const uint64_t x_hilo = umma_desc_sw128(hi_addr + MT_A_BYTES);        // 32 rows: x hi | x lo
-                const uint32_t lo_tmem = tmem_base + MT_TM_LO + ls * MT_TM_LSLOT + t * MT_BK;
-                tc_mbar_wait(bar_raw_full + rs, ruse & 1);
+                const uint32_t ls = it % MT_L, luse = it / MT_L;
+                const uint64_t x_hilo = umma_desc_sw128(x_base + ls * MT_XSLOT);        // 32 rows: x hi | x lo
+                const uint32_t a_tmem = tmem_base + MT_TM_OP + ls * MT_TM_SLOT + t * (2 * MT_BK);
                 tc_mbar_wait(bar_lo_full + ls, luse & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                // one elected lane issues; the block is executed convergently so that every operand can live in the
-                // uniform datapath (a divergent `if (lane == 0)` costs an ELECT + R2UR.BROADCAST chain per instruction)
-                mt_issue_ktile(d_tmem, w_hi, x_hilo, lo_tmem, kt ? 1u : 0u, tc_smem_u32(bar_raw_empty + rs),
-                               tc_smem_u32(bar_lo_empty + ls));
+                mt_issue_ktile(d_tmem, a_tmem, x_hilo, kt ? 1u : 0u, tc_smem_u32(bar_lo_empty + ls));
                 if (kt == MT_KT - 1) mt_commit_elected(tc_smem_u32(bar_tfull + as));
                 __syncwarp();
             }
@@ -251,7 +247,8 @@ ls_member_tc_kernel(const __grid_constant__ CUtensorMap map_w, const LsMemberTcP
             for (int kt = 0; kt < MT_KT; ++kt, ++it) {
                 if ((int)(it & 1) != grp) continue;
                 const uint32_t rs = it % MT_R, ruse = it / MT_R, ls = it % MT_L, luse = it / MT_L;
-                unsigned char* slot = raw_mem + (size_t)rs * MT_SLOT;
+                const unsigned char* slot = raw_mem + (size_t)rs * MT_A_BYTES;
+                unsigned char* xs = x_mem + (size_t)ls * MT_XSLOT;
                 if (luse > 0) tc_mbar_wait(bar_lo_empty + ls, (luse - 1) & 1);
                 tc_mbar_wait(bar_raw_full + rs, ruse & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -259,16 +256,20 @@ ls_member_tc_kernel(const __grid_constant__ CUtensorMap map_w, const LsMemberTcP
                 for (int t = 0; t < 2; ++t) {
                     // row r of tile t: 128 bytes, 16-byte chunk c stored at c ^ (r & 7)
                     const float4* row = reinterpret_cast<const float4*>(slot + (size_t)(t * 128 + r) * 128);
-                    float wl[32];
+                    float w[32];
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        const float4 w = row[c ^ (r & 7)];
-                        wl[4 * c] = f3_lo(w.x);
-                        wl[4 * c + 1] = f3_lo(w.y);
-                        wl[4 * c + 2] = f3_lo(w.z);
-                        wl[4 * c + 3] = f3_lo(w.w);
+                        const float4 v = row[c ^ (r & 7)];
+                        w[4 * c] = v.x;
+                        w[4 * c + 1] = v.y;
+                        w[4 * c + 2] = v.z;
+                        w[4 * c + 3] = v.w;
                     }
-                    f3_tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + MT_TM_LO + ls * MT_TM_LSLOT + t * MT_BK, wl);
+                    const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + MT_TM_OP + ls * MT_TM_SLOT + t * (2 * MT_BK);
+                    f3_tmem_st32(ta, w);                       // hi: the raw word, read truncated to TF32 by the tensor core
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) w[i] = f3_lo(w[i]);
+                    f3_tmem_st32(ta + MT_BK, w);               // lo
                 }
                 {
                     // activations k = kt * 32 + g * 4 + {0..3} of episode e (while the stores above are in flight)
@@ -296,9 +297,11 @@ ls_member_tc_kernel(const __grid_constant__ CUtensorMap map_w, const LsMemberTcP
                         lo[qq] = h - hi[qq];
                     }
                     const int off = e * 128 + ((g ^ (e & 7)) << 4);
-                    *reinterpret_cast<float4*>(slot + MT_A_BYTES + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<float4*>(slot + MT_A_BYTES + MT_X_BYTES + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    *reinterpret_cast<float4*>(xs + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<float4*>(xs + MT_X_BYTES + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
                 }
+                __syncwarp();
+                if (lane == 0) tc_mbar_arrive(bar_raw_empty + rs);           // the raw slot has been read: TMA may refill it
                 asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
                 asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic writes -> tensor core reads
                 asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -367,19 +370,18 @@ ls_member_tc_kernel(const __grid_constant__ CUtensorMap map_w, const LsMemberTcP
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
-                uint32_t hh[16], hl[16], lh[16];
+                uint32_t xh[16], xl[16];
                 const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + as * (2 * MT_ACC) + t * MT_ACC;
-                f3_tmem_ld16(ta, hh);
-                f3_tmem_ld16(ta + MT_NB, hl);
-                f3_tmem_ld16(ta + 2 * MT_NB, lh);
+                f3_tmem_ld16(ta, xh);
+                f3_tmem_ld16(ta + MT_NB, xl);
                 const int row = t * 128 + q * 32 + lane;
                 const float bias = b2[row];
                 float4* dst = reinterpret_cast<float4*>(hs + row * MT_NB);
                 const int sw = (row >> 1) & 3;
                 float h[16];
 #pragma unroll
-                for (int n = 0; n < 16; ++n)           // small terms first, then the bias (like fc2(h) + b)
-                    h[n] = ((__uint_as_float(lh[n]) + __uint_as_float(hl[n])) + __uint_as_float(hh[n])) + bias;
+                for (int n = 0; n < 16; ++n)           // the x_lo columns (small) first, then the bias (like fc2(h) + b)
+                    h[n] = (__uint_as_float(xl[n]) + __uint_as_float(xh[n])) + bias;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) dst[c ^ sw] = make_float4(h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
             }

@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(512) ls_member_l1stats_kernel(const float* __r
 // member forward (FP32 pipe)
 // ---------------------------------------------------------------------------------------------
 #ifndef LS_MEMBER_TC_DEFAULT
-#define LS_MEMBER_TC_DEFAULT 0
+#define LS_MEMBER_TC_DEFAULT 1                    // member forward: 1 = tensor cores beside the opponent kernel, 0 = FP32 pipe
 #endif
 #ifndef LS_GRID_OPP_DEFAULT
 #define LS_GRID_OPP_DEFAULT 0                     // 0 = one CTA per SM
@@ -711,6 +711,47 @@ __device__ __forceinline__ void op_umma(uint32_t d_tmem, uint64_t a_desc, uint64
         : "memory");
 }
 
+// The twelve MMAs of one k-tile (4 k-steps x {a_lo . b_hi, a_hi . b_lo, a_hi . b_hi}, small terms first) and the commit
+// that releases the stage, issued by ONE elected lane of a CONVERGED warp: inside a divergent `if (lane == 0)` every
+// tcgen05.mma costs an ELECT + R2UR.BROADCAST chain (~20 instructions, ~130 cycles of issue for 128 cycles of tensor
+// pipe), which held the tensor pipe at ~50 %.
+__device__ __forceinline__ void op_issue_ktile(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                               uint32_t accumulate, uint32_t bar_empty) {
+    asm volatile(
+        "{\n"
+        ".reg .pred pe, pa, pt;\n"
+        ".reg .b64 ah1, ah2, ah3, al1, al2, al3, bh1, bh2, bh3, bl1, bl2, bl3;\n"
+        "elect.sync _|pe, 0xffffffff;\n"
+        "setp.ne.b32 pa, %5, 0;\n"
+        "setp.eq.b32 pt, 0, 0;\n"
+        "add.s64 ah1, %1, 2;\n add.s64 ah2, %1, 4;\n add.s64 ah3, %1, 6;\n"
+        "add.s64 al1, %2, 2;\n add.s64 al2, %2, 4;\n add.s64 al3, %2, 6;\n"
+        "add.s64 bh1, %3, 2;\n add.s64 bh2, %3, 4;\n add.s64 bh3, %3, 6;\n"
+        "add.s64 bl1, %4, 2;\n add.s64 bl2, %4, 4;\n add.s64 bl3, %4, 6;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %2, %3, %7, pa;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %4, %7, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %3, %7, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], al1, bh1, %7, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], ah1, bl1, %7, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], ah1, bh1, %7, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], al2, bh2, %7, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], ah2, bl2, %7, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], ah2, bh2, %7, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], al3, bh3, %7, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], ah3, bl3, %7, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], ah3, bh3, %7, pt;\n"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(accumulate), "r"(bar_empty), "r"(OP_IDESC)
+        : "memory");
+}
+__device__ __forceinline__ void op_commit_elected(uint32_t bar) {
+    asm volatile(
+        "{\n.reg .pred pe;\nelect.sync _|pe, 0xffffffff;\n"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(bar)
+        : "memory");
+}
+
 // One producer thread's share of an A tile: 16-byte chunk c (4 activations) of k-tile kt for its FOUR
 // episode rows lane + 32 j: relu(LN1(W1 x + b1)), split into TF32 hi + lo and stored K-major with the
 // 128-byte swizzle the UMMA descriptor expects (chunk c of row r at c ^ (r & 7)).  The weight loads are
@@ -1047,6 +1088,7 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
         }
     } else {
         // ===================== MMA issuer =====================
+        const uint32_t stage_base = tc_smem_u32(stage_mem);
         uint32_t it = 0, pass = 0;
         for (int job = job0; job < p.n_jobs; job += job_stride, ++pass) {
             const uint32_t as = pass & 1, ause = pass >> 1;
@@ -1057,21 +1099,14 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
                 const uint32_t st = it % Geo::STAGES, use = it / Geo::STAGES;
                 tc_mbar_wait(bar_full + st, use & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                if (lane == 0) {
-                    const uint32_t s_addr = tc_smem_u32(stage_mem + (size_t)st * Geo::STAGE_BYTES);
-                    const uint64_t a_hi = umma_desc_sw128(s_addr);
-                    const uint64_t a_lo = umma_desc_sw128(s_addr + OP_A_BYTES);
-                    const uint64_t b_hi = umma_desc_sw128(s_addr + 2 * OP_A_BYTES);
-                    const uint64_t b_lo = umma_desc_sw128(s_addr + 2 * OP_A_BYTES + Geo::B_BYTES);
-#pragma unroll
-                    for (int k8 = 0; k8 < OP_BK / 8; ++k8) {
-                        const uint64_t ko = (uint64_t)(k8 * 2);           // 8 tf32 = 32 bytes
-                        op_umma(d_tmem, a_lo + ko, b_hi + ko, (kt | k8) ? 1u : 0u);   // small terms first
-                        op_umma(d_tmem, a_hi + ko, b_lo + ko, 1u);
-                        op_umma(d_tmem, a_hi + ko, b_hi + ko, 1u);
-                    }
-                    umma_commit(bar_empty + st);
-                    if (kt == OP_KT - 1) umma_commit(bar_tfull + as);
+                {
+                    // issued by one elected lane of the converged warp (see op_issue_ktile)
+                    const uint32_t s_addr = stage_base + st * Geo::STAGE_BYTES;
+                    op_issue_ktile(d_tmem, umma_desc_sw128(s_addr), umma_desc_sw128(s_addr + OP_A_BYTES),
+                                   umma_desc_sw128(s_addr + 2 * OP_A_BYTES),
+                                   umma_desc_sw128(s_addr + 2 * OP_A_BYTES + Geo::B_BYTES), kt ? 1u : 0u,
+                                   tc_smem_u32(bar_empty + st));
+                    if (kt == OP_KT - 1) op_commit_elected(tc_smem_u32(bar_tfull + as));
                 }
                 __syncwarp();
             }
@@ -1093,7 +1128,37 @@ namespace cev {
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-int rollout_lockstep_launches(int n_cycles) { return 4 + 3 * n_cycles; }
+static int ls_member_tc_enabled() {
+    static const int v = getenv("CEV_LS_MEMBER_TC") ? atoi(getenv("CEV_LS_MEMBER_TC")) : LS_MEMBER_TC_DEFAULT;
+    return v;
+}
+
+// opponent preparation (2) [+ member layer-1 statistics] + initial states + 3 kernels per world step
+int rollout_lockstep_launches(int n_cycles) { return 3 + (ls_member_tc_enabled() ? 1 : 0) + 3 * n_cycles; }
+
+// How the SMs are shared out between the two persistent kernels of a world step (tensor-core member form).
+// The opponent kernel is bound by the tensor pipe of the SMs it gets (~20 us per 128-episode job, ~15 us to get
+// going); a member job streams 512 KB and takes ~8.6 us on its SM until the HBM rate (~6 TB/s over all member CTAs)
+// becomes the limit.  Both end when their slowest CTA ends, so the split that minimises the later of the two is
+// found by trying every one (148 candidates, host side).
+static void ls_split_sms(int n_sm, int opp_jobs, int mem_jobs, int* g_opp, int* g_mem) {
+    double best = 1e30;
+    int bo = n_sm / 2;
+    for (int g = 1; g < n_sm; ++g) {
+        const int gm = n_sm - g;
+        const int mg = mem_jobs < gm ? mem_jobs : gm, og = opp_jobs < g ? opp_jobs : g;
+        const double t_job_mem = fmax(8.6, mg * 0.0873);
+        const double t_opp = 15.0 + 20.0 * ((opp_jobs + og - 1) / og);
+        const double t_mem = 4.0 + t_job_mem * ((mem_jobs + mg - 1) / mg);
+        const double t = fmax(t_opp, t_mem);
+        if (t < best - 1e-9) {
+            best = t;
+            bo = g;
+        }
+    }
+    *g_opp = bo;
+    *g_mem = n_sm - bo;
+}
 
 int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t stream) {
     if (p.P <= 0 || p.K <= 0 || p.E <= 0) return CEV_OK;
@@ -1141,7 +1206,7 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
     ls_l1stats_kernel<<<2 * p.K, 512, 0, stream>>>(pp);
 
     // ---- member form: 1 = tensor cores, persistent, beside the opponent kernel (ls_member_tc.cuh); 0 = FP32 pipe ----
-    static const int member_tc = getenv("CEV_LS_MEMBER_TC") ? atoi(getenv("CEV_LS_MEMBER_TC")) : LS_MEMBER_TC_DEFAULT;
+    const int member_tc = ls_member_tc_enabled();
     if (member_tc)
         ls_member_l1stats_kernel<<<p.P, 512, 0, stream>>>(p.members, p.member_pitch, seat_in_dim(ms), b.ml1stats);
 
@@ -1252,14 +1317,22 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
     tp.l1stats = b.ml1stats;
     tp.status = p.status;
     int mem_grid = tp.n_jobs < h->n_sm ? tp.n_jobs : h->n_sm;
-    if (member_tc) {
-        // The SMs are shared out between the two persistent kernels: the member kernel is bound by the HBM stream
-        // and keeps its rate on about half of the SMs, the opponent kernel is bound by the tensor pipe of the SMs
-        // it gets.  CEV_LS_GRID_OPP / CEV_LS_GRID_MEM override the split (development aid).
-        static const int g_opp = getenv("CEV_LS_GRID_OPP") ? atoi(getenv("CEV_LS_GRID_OPP")) : LS_GRID_OPP_DEFAULT;
-        static const int g_mem = getenv("CEV_LS_GRID_MEM") ? atoi(getenv("CEV_LS_GRID_MEM")) : LS_GRID_MEM_DEFAULT;
-        if (g_opp > 0 && g_opp < opp_grid) opp_grid = g_opp;
-        if (g_mem > 0 && g_mem < mem_grid) mem_grid = g_mem;
+    static const int want_fork = getenv("CEV_LS_FORK") ? atoi(getenv("CEV_LS_FORK")) : (member_tc ? 1 : 0);
+    // The two forwards of a world step are independent (same observations).  FP32 member form: two streams let the
+    // block scheduler fill one kernel's tail with the other's CTAs (+4 % at 1024 members, -3 % at 4096: opt-in).
+    // Tensor-core member form: both kernels are persistent and get a share of the SMs each, so the HBM stream of the
+    // member rows runs under the opponents' MMAs (default).
+    const bool fork = want_fork && !h->timing_on;
+    if (member_tc && fork) {
+        // CEV_LS_GRID_OPP / CEV_LS_GRID_MEM override the split (development aid)
+        static const int g_opp_env = getenv("CEV_LS_GRID_OPP") ? atoi(getenv("CEV_LS_GRID_OPP")) : LS_GRID_OPP_DEFAULT;
+        static const int g_mem_env = getenv("CEV_LS_GRID_MEM") ? atoi(getenv("CEV_LS_GRID_MEM")) : LS_GRID_MEM_DEFAULT;
+        int g_opp = 0, g_mem = 0;
+        ls_split_sms(h->n_sm, op.n_jobs, tp.n_jobs, &g_opp, &g_mem);
+        if (g_opp_env > 0) g_opp = g_opp_env;
+        if (g_mem_env > 0) g_mem = g_mem_env;
+        if (g_opp < opp_grid) opp_grid = g_opp;
+        if (g_mem < mem_grid) mem_grid = g_mem;
     }
 
     // development aids: CEV_LS_SKIP bit 0 = no opponent kernel, bit 1 = no member kernel (timing only,
@@ -1274,12 +1347,6 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
                                       (int)LsMemberSmem::total + member_pad));
         pad_configured = true;
     }
-    static const int want_fork = getenv("CEV_LS_FORK") ? atoi(getenv("CEV_LS_FORK")) : (member_tc ? 1 : 0);
-    // The two forwards of a world step are independent (same observations), use different pipes
-    // (tensor vs FP32/HBM) and both end in a partial wave, so running them on two streams lets the
-    // block scheduler fill one kernel's tail with the other's CTAs.  Measured: +4 % at 1024 members,
-    // -3 % at 4096 (the 227 KB opponent CTAs and 107 KB member CTAs cannot share an SM), so it is opt-in.
-    const bool fork = want_fork && !h->timing_on;
     if (fork && !h->side_stream) {
         CEV_CUDA(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
         CEV_CUDA(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
