@@ -31,6 +31,15 @@ class RolloutCfg(Structure):
                 ("variant", c_int32), ("reserved", c_int32)]
 
 
+class RolloutRole(Structure):
+    """cev_rollout_role (include/coevonet_b200.h): one role of cev_mpe_rollout_roles_f32."""
+    _fields_ = [("member_seat", c_int32), ("reserved", c_int32),
+                ("members", c_void_p), ("member_pitch", c_int64),
+                ("opp_a", c_void_p), ("opp_a_pitch", c_int64),
+                ("opp_b", c_void_p), ("opp_b_pitch", c_int64),
+                ("init", c_void_p), ("out", c_void_p)]
+
+
 class CevError(RuntimeError):
     pass
 
@@ -49,6 +58,8 @@ _SIGNATURES = {
                                     c_void_p, c_int64, c_void_p, c_int64, c_int,
                                     c_void_p, c_int, c_int, POINTER(RolloutCfg),
                                     c_void_p, c_void_p, c_void_p]),
+    "cev_mpe_rollout_roles_f32": (c_int, [c_void_p, c_int, POINTER(RolloutRole), c_int, c_int, c_int, c_int,
+                                          POINTER(RolloutCfg), c_void_p, c_void_p]),
     "cev_mpe_rollout_trace_f32": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64,
                                           c_void_p, c_int64, c_void_p, c_int64, c_int,
                                           c_void_p, c_int, c_int, POINTER(RolloutCfg),

@@ -57,6 +57,7 @@ int cev_create(int device, cev_handle** out) {
     h->ls_workspace_bytes = 0;
     h->side_stream = nullptr;
     h->fork_ev = h->join_ev = nullptr;
+    h->env_stream = nullptr;
     h->timing_on = 0;
     h->timing_n[0] = h->timing_n[1] = 0;
     h->timing_ev[0] = h->timing_ev[1] = nullptr;
@@ -77,6 +78,17 @@ int cev_destroy(cev_handle* h) {
         cudaStreamDestroy(h->side_stream);
         cudaEventDestroy(h->fork_ev);
         cudaEventDestroy(h->join_ev);
+    }
+    if (h->env_stream) {
+        cudaStreamDestroy(h->env_stream);
+        cudaStreamDestroy(h->opp_stream2[0]);
+        cudaStreamDestroy(h->opp_stream2[1]);
+        cudaStreamDestroy(h->mem_stream2);
+        for (int r = 0; r < CEV_MAX_ROLES; ++r) {
+            cudaEventDestroy(h->ev_opp[r]);
+            cudaEventDestroy(h->ev_mem[r]);
+            cudaEventDestroy(h->ev_env[r]);
+        }
     }
     for (int k = 0; k < 2; ++k)
         if (h->timing_ev[k]) {
@@ -180,6 +192,61 @@ int cev_mpe_rollout_f32(cev_handle* h, int member_seat, const float* members, in
     g.pos_first = cfg->integrate_pos_first;
     g.N = (int64_t)P * K * E;
     return launch_rollout_generic(h, g, st);
+}
+
+int cev_mpe_rollout_roles_f32(cev_handle* h, int n_roles, const cev_rollout_role* roles, int P, int K, int init_shared,
+                              int E, const cev_rollout_cfg* cfg, int32_t* status, cev_stream stream) {
+    CEV_REQUIRE(h && roles, "mpe_rollout_roles: null pointer");
+    CEV_REQUIRE(n_roles >= 1 && n_roles <= CEV_MAX_ROLES, "mpe_rollout_roles: n_roles must be 1..%d", CEV_MAX_ROLES);
+    CEV_REQUIRE(P >= 0 && K >= 1 && E >= 1, "mpe_rollout_roles: need P >= 0, K >= 1, E >= 1");
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    for (int r = 0; r < n_roles; ++r)
+        CEV_REQUIRE(roles[r].members && roles[r].opp_a && roles[r].opp_b && roles[r].init && roles[r].out,
+                    "mpe_rollout_roles: null pointer in role %d", r);
+    if (P == 0) return CEV_OK;
+    const int variant = rollout_plan(h, P, K, E, cfg->variant);
+    if (variant != 3) {
+        for (int r = 0; r < n_roles; ++r) {
+            rc = cev_mpe_rollout_f32(h, roles[r].member_seat, roles[r].members, P, roles[r].member_pitch, roles[r].opp_a,
+                                     roles[r].opp_a_pitch, roles[r].opp_b, roles[r].opp_b_pitch, K, roles[r].init,
+                                     init_shared, E, cfg, roles[r].out, status, stream);
+            if (rc) return rc;
+        }
+        return CEV_OK;
+    }
+    ClusterParams ps[CEV_MAX_ROLES];
+    for (int r = 0; r < n_roles; ++r) {
+        const cev_rollout_role& q = roles[r];
+        CEV_REQUIRE(q.member_seat >= 0 && q.member_seat <= 2, "mpe_rollout_roles: member_seat must be 0..2");
+        const int other[2] = {q.member_seat == 0 ? 1 : 0, q.member_seat == 2 ? 1 : 2};
+        CEV_REQUIRE(q.member_pitch >= fc_offsets(seat_in_dim(q.member_seat)).total && q.member_pitch % 4 == 0 &&
+                        q.opp_a_pitch >= fc_offsets(seat_in_dim(other[0])).total && q.opp_a_pitch % 4 == 0 &&
+                        q.opp_b_pitch >= fc_offsets(seat_in_dim(other[1])).total && q.opp_b_pitch % 4 == 0,
+                    "mpe_rollout_roles: pitch too small / not a multiple of 4");
+        CEV_REQUIRE(aligned16(q.members) && aligned16(q.opp_a) && aligned16(q.opp_b),
+                    "mpe_rollout_roles: rows must be 16B aligned");
+        ClusterParams& p = ps[r];
+        p = ClusterParams{};
+        p.members = q.members;
+        p.member_pitch = q.member_pitch;
+        p.P = P;
+        p.opp[0] = q.opp_a;
+        p.opp[1] = q.opp_b;
+        p.opp_pitch[0] = q.opp_a_pitch;
+        p.opp_pitch[1] = q.opp_b_pitch;
+        p.K = K;
+        p.member_seat = q.member_seat;
+        p.init = q.init;
+        p.init_shared = init_shared;
+        p.E = E;
+        p.out = q.out;
+        p.status = status;
+        p.n_cycles = cfg->n_cycles;
+        p.pos_first = cfg->integrate_pos_first;
+    }
+    CEV_GUARD(h);
+    return launch_rollout_lockstep_roles(h, ps, n_roles, (cudaStream_t)stream);
 }
 
 int cev_mpe_rollout_trace_f32(cev_handle* h, int member_seat, const float* members, int P, int64_t member_pitch,

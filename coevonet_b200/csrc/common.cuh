@@ -287,6 +287,8 @@ __host__ __device__ __forceinline__ uint32_t noise_tag(int kind, int role) {
 
 constexpr int CEV_TIMING_MAX = 4096;
 
+#define CEV_MAX_ROLES 3
+
 // per-handle state
 struct cev_handle {
     int device;
@@ -300,6 +302,9 @@ struct cev_handle {
     size_t ls_workspace_bytes;
     cudaStream_t side_stream;           // the opponent kernel of the lockstep rollout runs beside the member kernel
     cudaEvent_t fork_ev, join_ev;
+    // several roles in one lockstep pass (launch_rollout_lockstep_roles): environment steps on a third stream
+    cudaStream_t env_stream, opp_stream2[2], mem_stream2;
+    cudaEvent_t ev_opp[CEV_MAX_ROLES], ev_mem[CEV_MAX_ROLES], ev_env[CEV_MAX_ROLES];
     // optional per-kernel timing of the lockstep rollout (cev_kernel_timing_*): CUDA events recorded
     // around every member / opponent kernel launch on the launch stream
     int timing_on;
@@ -347,6 +352,7 @@ int launch_rollout_generic(cev_handle* h, const GenericParams& p, cudaStream_t s
 int launch_rollout_cluster(cev_handle* h, const ClusterParams& p, cudaStream_t stream);
 int rollout_cluster_max_clusters(int device);
 int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t stream);
+int launch_rollout_lockstep_roles(cev_handle* h, const ClusterParams* ps, int n_roles, cudaStream_t stream);
 int rollout_lockstep_launches(int n_cycles);
 int launch_deepqn_fc_tc(cev_handle* h, const float* members, int64_t pitch, int P, int B, int n_act, int f1w_off,
                         int f1b_off, int ow_off, int ob_off, const float* act3, float* logits, int32_t* actions,

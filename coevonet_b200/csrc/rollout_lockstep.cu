@@ -1160,27 +1160,20 @@ static void ls_split_sms(int n_sm, int opp_jobs, int mem_jobs, int* g_opp, int* 
     *g_mem = n_sm - bo;
 }
 
-int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t stream) {
-    if (p.P <= 0 || p.K <= 0 || p.E <= 0) return CEV_OK;
-    EncodeTiledFn encode = get_encode_fn();
-    if (!encode) {
-        set_error("rollout_lockstep: cuTensorMapEncodeTiled is not available from the driver");
-        return CEV_ERR_UNSUPPORTED;
-    }
-    const int64_t N = (int64_t)p.P * p.K * p.E;
-    const size_t need = ls_carve(nullptr, N, p.K, p.P, nullptr);
-    if (h->ls_workspace_bytes < need) {
-        if (h->ls_workspace) CEV_CUDA(cudaFree(h->ls_workspace));
-        h->ls_workspace = nullptr;
-        h->ls_workspace_bytes = 0;
-        CEV_CUDA(cudaMalloc(&h->ls_workspace, need));
-        h->ls_workspace_bytes = need;
-    }
+// Everything one role's rollout needs on the device: workspace views, tensor maps, kernel parameter blocks.
+struct LsRoleCtx {
     LsBuffers b;
-    ls_carve(h->ls_workspace, N, p.K, p.P, &b);
-    const int ms = p.member_seat;
-    const int seat_of[2] = {ms == 0 ? 1 : 0, ms == 2 ? 1 : 2};
+    CUtensorMap map_w2, map_b, map_wtc;
+    LsEnvParams ep;
+    LsMemberParams mp;
+    LsOppParams op;
+    LsMemberTcParams tp;
+    int env_blocks;
+    int64_t member_ctas;
+    int ms;
+};
 
+static int ls_configure(cev_handle* h) {
     static bool configured[16] = {};
     if (h->device < 16 && !configured[h->device]) {
         CEV_CUDA(cudaFuncSetAttribute(ls_member_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1191,6 +1184,34 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
         CEV_CUDA(cudaFuncSetAttribute(ls_member_tc_kernel<IN_GOOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MT_SMEM));
         configured[h->device] = true;
     }
+    return CEV_OK;
+}
+
+static int ls_reserve(cev_handle* h, size_t need) {
+    if (h->ls_workspace_bytes < need) {
+        if (h->ls_workspace) CEV_CUDA(cudaFree(h->ls_workspace));
+        h->ls_workspace = nullptr;
+        h->ls_workspace_bytes = 0;
+        CEV_CUDA(cudaMalloc(&h->ls_workspace, need));
+        h->ls_workspace_bytes = need;
+    }
+    return CEV_OK;
+}
+
+// Launches the once-per-rollout preparation of one role on `stream` (TF32 split of the opponents' fc2, layer-1
+// statistics of the opponents and, for the tensor-core member form, of every member row) and fills the context.
+static int ls_build_role(cev_handle* h, const ClusterParams& p, void* ws, int member_tc, cudaStream_t stream, LsRoleCtx* c) {
+    EncodeTiledFn encode = get_encode_fn();
+    if (!encode) {
+        set_error("rollout_lockstep: cuTensorMapEncodeTiled is not available from the driver");
+        return CEV_ERR_UNSUPPORTED;
+    }
+    const int64_t N = (int64_t)p.P * p.K * p.E;
+    LsBuffers& b = c->b;
+    ls_carve(ws, N, p.K, p.P, &b);
+    const int ms = p.member_seat;
+    c->ms = ms;
+    const int seat_of[2] = {ms == 0 ? 1 : 0, ms == 2 ? 1 : 2};
 
     // ---- opponents: TF32 split + layer-1 statistics ------------------------------------------
     LsPrepParams pp{};
@@ -1204,36 +1225,30 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
     pp.l1stats = b.l1stats;
     ls_split_w2_kernel<<<dim3(32, 2 * p.K), 256, 0, stream>>>(pp);
     ls_l1stats_kernel<<<2 * p.K, 512, 0, stream>>>(pp);
-
-    // ---- member form: 1 = tensor cores, persistent, beside the opponent kernel (ls_member_tc.cuh); 0 = FP32 pipe ----
-    const int member_tc = ls_member_tc_enabled();
     if (member_tc)
         ls_member_l1stats_kernel<<<p.P, 512, 0, stream>>>(p.members, p.member_pitch, seat_in_dim(ms), b.ml1stats);
 
     // ---- tensor maps ---------------------------------------------------------------------------
-    CUtensorMap map_w2, map_b, map_wtc;
+    const FcOffsets om = fc_offsets(seat_in_dim(ms));
     if (member_tc) {
-        const FcOffsets om = fc_offsets(seat_in_dim(ms));
         cuuint64_t dims[3] = {(cuuint64_t)H1, (cuuint64_t)H2, (cuuint64_t)p.P};
         cuuint64_t strides[2] = {(cuuint64_t)H1 * 4, (cuuint64_t)p.member_pitch * 4};
         cuuint32_t box[3] = {MT_BK, H2, 1};
         cuuint32_t estr[3] = {1, 1, 1};
-        CUresult r = encode(&map_wtc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.members + om.fc2w), dims,
+        CUresult r = encode(&c->map_wtc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.members + om.fc2w), dims,
                             strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             set_error("rollout_lockstep: cuTensorMapEncodeTiled(member fc2, tensor-core form) failed with %d", (int)r);
             return CEV_ERR_CUDA;
         }
-    }
-    {
-        const FcOffsets om = fc_offsets(seat_in_dim(ms));
+    } else {
         cuuint64_t dims[3] = {(cuuint64_t)H1, (cuuint64_t)H2, (cuuint64_t)p.P};
         cuuint64_t strides[2] = {(cuuint64_t)H1 * 4, (cuuint64_t)p.member_pitch * 4};
         cuuint32_t box[3] = {LS_TILE_K, LS_TILE_ROWS, 1};
         cuuint32_t estr[3] = {1, 1, 1};
         static const int l2p = getenv("CEV_LS_L2P") ? atoi(getenv("CEV_LS_L2P")) : 128;
-        CUresult r = encode(&map_w2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.members + om.fc2w), dims,
+        CUresult r = encode(&c->map_w2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.members + om.fc2w), dims,
                             strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                             l2p == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
                                        : (l2p == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B),
@@ -1248,7 +1263,7 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
         cuuint64_t strides[1] = {(cuuint64_t)H1 * 4};
         cuuint32_t box[2] = {OP_BK, OP_BN};
         cuuint32_t estr[2] = {1, 1};
-        CUresult r = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, b.w2split, dims, strides, box, estr,
+        CUresult r = encode(&c->map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, b.w2split, dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
@@ -1258,7 +1273,8 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
     }
 
     // ---- per-step parameter blocks ---------------------------------------------------------------
-    LsEnvParams ep{};
+    LsEnvParams& ep = c->ep;
+    ep = LsEnvParams{};
     ep.b = b;
     ep.N = N;
     ep.K = p.K;
@@ -1267,9 +1283,10 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
     ep.pos_first = p.pos_first;
     ep.init = p.init;
     ep.out = p.out;
-    const int env_blocks = (int)((N + 255) / 256);
+    c->env_blocks = (int)((N + 255) / 256);
 
-    LsMemberParams mp{};
+    LsMemberParams& mp = c->mp;
+    mp = LsMemberParams{};
     mp.members = p.members;
     mp.pitch = p.member_pitch;
     mp.KE = p.K * p.E;
@@ -1280,10 +1297,11 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
     mp.act = b.act + (int64_t)ms * N;
     mp.gap = b.gap + (int64_t)ms * N;
     mp.status = p.status;
-    const int64_t member_ctas = (int64_t)p.P * mp.n_chunks;
-    CEV_REQUIRE(member_ctas < (1ll << 31), "rollout_lockstep: too many member tiles");
+    c->member_ctas = (int64_t)p.P * mp.n_chunks;
+    CEV_REQUIRE(c->member_ctas < (1ll << 31), "rollout_lockstep: too many member tiles");
 
-    LsOppParams op{};
+    LsOppParams& op = c->op;
+    op = LsOppParams{};
     for (int oi = 0; oi < 2; ++oi) {
         op.opp[oi] = p.opp[oi];
         op.opp_pitch[oi] = p.opp_pitch[oi];
@@ -1292,8 +1310,7 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
     op.K = p.K;
     op.E = p.E;
     op.PE = (int64_t)p.P * p.E;
-    const int rows_per_job = OP_BM;
-    op.n_tiles = (int)((op.PE + rows_per_job - 1) / rows_per_job);
+    op.n_tiles = (int)((op.PE + OP_BM - 1) / OP_BM);
     op.n_jobs = 2 * p.K * op.n_tiles;
     op.N = N;
     op.obs = b.obs;
@@ -1301,21 +1318,48 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
     op.gap = b.gap;
     op.l1stats = b.l1stats;
     op.status = p.status;
-    int opp_grid = op.n_jobs < h->n_sm ? op.n_jobs : h->n_sm;
 
-    LsMemberTcParams tp{};
+    LsMemberTcParams& tp = c->tp;
+    tp = LsMemberTcParams{};
     tp.members = p.members;
     tp.pitch = p.member_pitch;
     tp.KE = mp.KE;
     tp.n_chunks = mp.n_chunks;
     tp.seat = ms;
-    tp.n_jobs = (int)member_ctas;
+    tp.n_jobs = (int)c->member_ctas;
     tp.N = N;
     tp.obs = mp.obs;
     tp.act = mp.act;
     tp.gap = mp.gap;
     tp.l1stats = b.ml1stats;
     tp.status = p.status;
+    return CEV_OK;
+}
+
+static void ls_launch_member_tc(const LsRoleCtx& c, int grid, cudaStream_t stream) {
+    if (c.ms == 0) ls_member_tc_kernel<IN_ADV><<<grid, MT_THREADS, MT_SMEM, stream>>>(c.map_wtc, c.tp);
+    else ls_member_tc_kernel<IN_GOOD><<<grid, MT_THREADS, MT_SMEM, stream>>>(c.map_wtc, c.tp);
+}
+
+int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t stream) {
+    if (p.P <= 0 || p.K <= 0 || p.E <= 0) return CEV_OK;
+    const int64_t N = (int64_t)p.P * p.K * p.E;
+    int rc = ls_reserve(h, ls_carve(nullptr, N, p.K, p.P, nullptr));
+    if (rc) return rc;
+    rc = ls_configure(h);
+    if (rc) return rc;
+    const int member_tc = ls_member_tc_enabled();
+    LsRoleCtx ctx;
+    rc = ls_build_role(h, p, h->ls_workspace, member_tc, stream, &ctx);
+    if (rc) return rc;
+    LsEnvParams& ep = ctx.ep;
+    LsMemberParams& mp = ctx.mp;
+    LsOppParams& op = ctx.op;
+    LsMemberTcParams& tp = ctx.tp;
+    const int ms = ctx.ms;
+    const int env_blocks = ctx.env_blocks;
+    const int64_t member_ctas = ctx.member_ctas;
+    int opp_grid = op.n_jobs < h->n_sm ? op.n_jobs : h->n_sm;
     int mem_grid = tp.n_jobs < h->n_sm ? tp.n_jobs : h->n_sm;
     static const int want_fork = getenv("CEV_LS_FORK") ? atoi(getenv("CEV_LS_FORK")) : (member_tc ? 1 : 0);
     // The two forwards of a world step are independent (same observations).  FP32 member form: two streams let the
@@ -1373,21 +1417,20 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
             if (fork) {
                 CEV_CUDA(cudaEventRecord(h->fork_ev, stream));
                 CEV_CUDA(cudaStreamWaitEvent(h->side_stream, h->fork_ev, 0));
-                ls_opp_kernel<<<opp_grid, OP_THREADS, OP_SMEM, h->side_stream>>>(map_b, op);
+                ls_opp_kernel<<<opp_grid, OP_THREADS, OP_SMEM, h->side_stream>>>(ctx.map_b, op);
                 CEV_CUDA(cudaEventRecord(h->join_ev, h->side_stream));
             } else {
                 tick(1, 0);
-                ls_opp_kernel<<<opp_grid, OP_THREADS, OP_SMEM, stream>>>(map_b, op);
+                ls_opp_kernel<<<opp_grid, OP_THREADS, OP_SMEM, stream>>>(ctx.map_b, op);
                 tick(1, 1);
             }
         }
         if (!(skip & 2)) {
             tick(0, 0);
             if (member_tc) {
-                if (ms == 0) ls_member_tc_kernel<IN_ADV><<<mem_grid, MT_THREADS, MT_SMEM, stream>>>(map_wtc, tp);
-                else ls_member_tc_kernel<IN_GOOD><<<mem_grid, MT_THREADS, MT_SMEM, stream>>>(map_wtc, tp);
+                ls_launch_member_tc(ctx, mem_grid, stream);
             } else {
-                ls_member_kernel<<<(unsigned)member_ctas, LS_MT, LsMemberSmem::total + member_pad, stream>>>(map_w2, mp);
+                ls_member_kernel<<<(unsigned)member_ctas, LS_MT, LsMemberSmem::total + member_pad, stream>>>(ctx.map_w2, mp);
             }
             tick(0, 1);
         }
@@ -1396,6 +1439,107 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
         ls_env_step_kernel<<<env_blocks, 256, 0, stream>>>(ep);
     }
     return check_cuda(cudaGetLastError(), "rollout_lockstep launch");
+}
+
+// The evaluations of several roles of one generation (the reference's three role loops, evolutionary_strategy.py:
+// 236-251, genetic_algorithm.py:125-217) as ONE lockstep pass: per world step the roles' member kernels run back to
+// back on the launch stream, their opponent kernels back to back on a second stream and their environment steps
+// on a third (high priority), each waiting only for the two kernels of ITS role.  With one role per CUDA stream the
+// block scheduler mixes the six persistent kernels at random (two member kernels sharing the HBM stream while the
+// tensor pipes idle, then the reverse); here there is always exactly one member kernel on its share of the SMs and
+// one opponent kernel on the rest, and a role's environment step hides under the next role's kernels.
+// Same results as n_roles calls of launch_rollout_lockstep.  Every role has the same P, K, E.
+int launch_rollout_lockstep_roles(cev_handle* h, const ClusterParams* ps, int n_roles, cudaStream_t stream) {
+    if (n_roles <= 0) return CEV_OK;
+    const ClusterParams& p0 = ps[0];
+    if (p0.P <= 0 || p0.K <= 0 || p0.E <= 0) return CEV_OK;
+    const int member_tc = ls_member_tc_enabled();
+    static const int want_roles = getenv("CEV_LS_ROLES") ? atoi(getenv("CEV_LS_ROLES")) : 1;
+    if (!member_tc || h->timing_on || !want_roles || n_roles > CEV_MAX_ROLES) {
+        for (int r = 0; r < n_roles; ++r) {
+            const int rc = launch_rollout_lockstep(h, ps[r], stream);
+            if (rc) return rc;
+        }
+        return CEV_OK;
+    }
+    const int64_t N = (int64_t)p0.P * p0.K * p0.E;
+    const size_t per_role = ls_align(ls_carve(nullptr, N, p0.K, p0.P, nullptr));
+    int rc = ls_reserve(h, per_role * n_roles);
+    if (rc) return rc;
+    rc = ls_configure(h);
+    if (rc) return rc;
+    if (!h->side_stream) {
+        CEV_CUDA(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+        CEV_CUDA(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
+        CEV_CUDA(cudaEventCreateWithFlags(&h->join_ev, cudaEventDisableTiming));
+    }
+    if (!h->env_stream) {
+        // priorities: environment steps first (tiny, on the critical path of their role), then the opponent kernels
+        // (they only ever ask for their share of the SMs), then the member kernels, which take what is left
+        int lo = 0, hi = 0;
+        CEV_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        const int mid = hi < lo ? lo - 1 : lo;
+        CEV_CUDA(cudaStreamCreateWithPriority(&h->env_stream, cudaStreamNonBlocking, hi));
+        CEV_CUDA(cudaStreamCreateWithPriority(&h->opp_stream2[0], cudaStreamNonBlocking, mid));
+        CEV_CUDA(cudaStreamCreateWithPriority(&h->opp_stream2[1], cudaStreamNonBlocking, mid));
+        CEV_CUDA(cudaStreamCreateWithPriority(&h->mem_stream2, cudaStreamNonBlocking, lo));
+        for (int r = 0; r < CEV_MAX_ROLES; ++r) {
+            CEV_CUDA(cudaEventCreateWithFlags(&h->ev_opp[r], cudaEventDisableTiming));
+            CEV_CUDA(cudaEventCreateWithFlags(&h->ev_mem[r], cudaEventDisableTiming));
+            CEV_CUDA(cudaEventCreateWithFlags(&h->ev_env[r], cudaEventDisableTiming));
+        }
+    }
+    LsRoleCtx ctx[CEV_MAX_ROLES];
+    for (int r = 0; r < n_roles; ++r) {
+        rc = ls_build_role(h, ps[r], static_cast<char*>(h->ls_workspace) + per_role * r, 1, stream, &ctx[r]);
+        if (rc) return rc;
+        ctx[r].ep.last = ps[r].n_cycles == 0;
+        ls_init_kernel<<<ctx[r].env_blocks, 256, 0, stream>>>(ctx[r].ep);
+    }
+    int opp_grid = 0, mem_grid = 0;
+    ls_split_sms(h->n_sm, ctx[0].op.n_jobs, ctx[0].tp.n_jobs, &opp_grid, &mem_grid);
+    static const int g_opp_env = getenv("CEV_LS_GRID_OPP") ? atoi(getenv("CEV_LS_GRID_OPP")) : LS_GRID_OPP_DEFAULT;
+    static const int g_mem_env = getenv("CEV_LS_GRID_MEM") ? atoi(getenv("CEV_LS_GRID_MEM")) : LS_GRID_MEM_DEFAULT;
+    if (g_opp_env > 0) opp_grid = g_opp_env;
+    if (g_mem_env > 0) mem_grid = g_mem_env;
+    if (ctx[0].op.n_jobs < opp_grid) opp_grid = ctx[0].op.n_jobs;
+    if (ctx[0].tp.n_jobs < mem_grid) mem_grid = ctx[0].tp.n_jobs;
+
+    // Consecutive kernels of one kind alternate between two streams, so the next role's CTAs move in as the previous
+    // role's CTAs retire (no idle tail at the end of every kernel, launch latency hidden).
+    static const int alt = getenv("CEV_LS_ALT") ? atoi(getenv("CEV_LS_ALT")) : 1;
+    cudaStream_t s_mem[2] = {stream, alt ? h->mem_stream2 : stream};
+    cudaStream_t s_opp[2] = {h->opp_stream2[0], alt ? h->opp_stream2[1] : h->opp_stream2[0]};
+    cudaStream_t s_env = h->env_stream;
+    CEV_CUDA(cudaEventRecord(h->fork_ev, stream));                  // preparation + initial states are on `stream`
+    CEV_CUDA(cudaStreamWaitEvent(s_opp[0], h->fork_ev, 0));
+    CEV_CUDA(cudaStreamWaitEvent(s_opp[1], h->fork_ev, 0));
+    CEV_CUDA(cudaStreamWaitEvent(s_mem[1], h->fork_ev, 0));
+    CEV_CUDA(cudaStreamWaitEvent(s_env, h->fork_ev, 0));
+    const int n_cycles = p0.n_cycles;
+    int i = 0;
+    for (int c = 0; c < n_cycles; ++c) {
+        for (int r = 0; r < n_roles; ++r, ++i) {
+            cudaStream_t so = s_opp[i & 1], sm = s_mem[i & 1];
+            if (c > 0) {                                            // this role's previous environment step
+                CEV_CUDA(cudaStreamWaitEvent(so, h->ev_env[r], 0));
+                CEV_CUDA(cudaStreamWaitEvent(sm, h->ev_env[r], 0));
+            }
+            ls_opp_kernel<<<opp_grid, OP_THREADS, OP_SMEM, so>>>(ctx[r].map_b, ctx[r].op);
+            CEV_CUDA(cudaEventRecord(h->ev_opp[r], so));
+            ls_launch_member_tc(ctx[r], mem_grid, sm);
+            CEV_CUDA(cudaEventRecord(h->ev_mem[r], sm));
+            CEV_CUDA(cudaStreamWaitEvent(s_env, h->ev_opp[r], 0));
+            CEV_CUDA(cudaStreamWaitEvent(s_env, h->ev_mem[r], 0));
+            ctx[r].ep.last = c == n_cycles - 1;
+            ls_env_step_kernel<<<ctx[r].env_blocks, 256, 0, s_env>>>(ctx[r].ep);
+            CEV_CUDA(cudaEventRecord(h->ev_env[r], s_env));
+        }
+    }
+    // join: the environment steps wait for every member / opponent kernel of their role, and s_env is in order
+    CEV_CUDA(cudaEventRecord(h->join_ev, s_env));
+    CEV_CUDA(cudaStreamWaitEvent(stream, h->join_ev, 0));
+    return check_cuda(cudaGetLastError(), "rollout_lockstep (roles) launch");
 }
 
 }  // namespace cev

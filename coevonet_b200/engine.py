@@ -159,6 +159,9 @@ class _EngineBase:
         self.overlap_roles = bool(getattr(args, "overlap_roles", True)) and self.device.type == "cuda"
         self._role_streams = None
         self._eval_stream = None
+        #: the roles' rollouts of a generation as ONE lockstep pass (cev_mpe_rollout_roles_f32) instead of one pass
+        #: per role on three streams: one member kernel and one opponent kernel share the SMs at any time
+        self.fused_roles = bool(getattr(args, "fused_roles", True)) and self.device.type == "cuda"
         #: ES update from the materialised members (K6 as an HBM-bound read) instead of regenerating the
         #: noise from the Philox key (K6 as ALU work); both are within fp32 rounding of each other
         self.update_from_members = bool(getattr(args, "update_from_members", True))
@@ -261,7 +264,9 @@ class _EngineBase:
 
         if self.device.type == "cuda":
             if self._eval_stream is None:
-                self._eval_stream = torch.cuda.Stream(device=self.device)
+                # high priority: the evaluation games are one small launch (a 4-CTA cluster) that must find four free
+                # SMs among the persistent rollout kernels of the next generation instead of waiting for their end
+                self._eval_stream = torch.cuda.Stream(device=self.device, priority=-1)
             main = torch.cuda.current_stream(self.device)
             self._eval_stream.wait_stream(main)
             with torch.cuda.stream(self._eval_stream):
@@ -329,6 +334,30 @@ class _EngineBase:
         else:
             for role in ROLES:
                 fn(role)
+
+    def _rollouts(self, specs, limit):
+        """K1 for the given (role, members, opp_a, opp_b, init) specs -> {role: out fp64 [n_local, K, E, 4]}."""
+        n_cycles = _limit_cycles(self.k, limit)
+        if self.fused_roles and self.k1_events is None and hasattr(self.k, "mpe_rollout_roles") and len(specs) > 1:
+            outs = self.k.mpe_rollout_roles(specs, n_cycles=n_cycles, pos_first=self.pos_first, status=self.status,
+                                            variant=self.variant)
+            return {spec[0]: out for spec, out in zip(specs, outs)}
+        res = {}
+
+        def one(role):
+            spec = next(sp for sp in specs if sp[0] == role)
+            if self.k1_events is not None:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+            res[role] = self.k.mpe_rollout(role, spec[1], spec[2], spec[3], spec[4], n_cycles=n_cycles,
+                                           pos_first=self.pos_first, status=self.status, variant=self.variant)
+            if self.k1_events is not None:
+                e1.record()
+                self.k1_events.append((e0, e1))
+
+        self._run_roles(one)
+        return res
 
     # -- checkpoint / resume (N2) ---------------------------------------------------------------
     def _base_state(self):
@@ -406,12 +435,10 @@ class GAEngine(_EngineBase):
         second = newest_first["agent_0"] if self.compat else newest_first["agent_1"]
         return newest_first["agent_0"], second
 
-    def _rollout_role(self, role, init):
-        """Local rewards + distances of one role (genetic_algorithm.py:125-217)."""
+    def _rollout_spec(self, role, init):
+        """(role, members, opp_a, opp_b, init) of one role's evaluation loop (genetic_algorithm.py:125-217)."""
         a = self.args
-        in_dim = layout.OBS_DIM[role]
         K = int(a.hof_size)
-        limit = a.max_timesteps_per_episode
         opp_a, opp_b = self._opponents(role)
         if self.compat and not getattr(a, "play_discarded_hof_games", False):
             # The reference plays hof_size games per member but OVERWRITES the reward each time
@@ -421,8 +448,13 @@ class GAEngine(_EngineBase):
             # that counts starts from the same state as in a reference run.
             opp_a, opp_b = opp_a[K - 1:K].contiguous(), opp_b[K - 1:K].contiguous()
             init = init[:, K - 1:K].contiguous()
-        out = self.k.mpe_rollout(role, self.pop[role], opp_a, opp_b, init, n_cycles=_limit_cycles(self.k, limit),
-                                 pos_first=self.pos_first, status=self.status, variant=self.variant)
+        return (role, self.pop[role], opp_a, opp_b, init)
+
+    def _finish_role(self, role, out):
+        """Local rewards + distances of one role from its rollout results."""
+        a = self.args
+        K = int(a.hof_size)
+        limit = a.max_timesteps_per_episode
         slot = self._role_slot(out, role, limit)                      # [n_local, K or 1, E]
         if self.compat:
             # only the LAST HoF game counts (reward overwritten, `=`), then / hof_size
@@ -431,8 +463,14 @@ class GAEngine(_EngineBase):
         else:
             reward = slot.mean(dim=(1, 2))
         # fitness sharing against the frozen founder (Appendix C #3)
-        dist_local = self.k.diversity_dist(self.pop[role], self.founder[role], in_dim)
+        dist_local = self.k.diversity_dist(self.pop[role], self.founder[role], layout.OBS_DIM[role])
         self._local[role] = (reward.contiguous(), dist_local)
+
+    def _rollout_role(self, role, init):
+        """Local rewards + distances of one role (genetic_algorithm.py:125-217)."""
+        spec = self._rollout_spec(role, init)
+        out = self._rollouts([spec], self.args.max_timesteps_per_episode)[role]
+        self._finish_role(role, out)
 
     def evaluate(self):
         """The three evaluation loops -> global fitness fp64[P] per role; one fused all-gather."""
@@ -441,7 +479,10 @@ class GAEngine(_EngineBase):
         # host-stream order of a reference run: role after role (genetic_algorithm.py:125-217)
         init = {r: self._initial_states(self.P, K, self.shard, ROLES.index(r) + 4 * self.gen) for r in ROLES}
         self._local = {}
-        self._run_roles(lambda role: self._rollout_role(role, init[role]))
+        specs = [self._rollout_spec(r, init[r]) for r in ROLES]
+        outs = self._rollouts(specs, a.max_timesteps_per_episode)
+        for r in ROLES:
+            self._finish_role(r, outs[r])
         packed = torch.stack([torch.stack([self._local[r][0].to(torch.float64),
                                            self._local[r][1].to(torch.float64)], dim=1) for r in ROLES], dim=1)
         allp = self.comm.all_gather_rows(packed.contiguous(), self.shard)          # [P, 3, 2]
@@ -598,7 +639,9 @@ class ESEngine(_EngineBase):
         if ref_init is None and self.init_mode == "reference":
             ref_init = self._reference_initial_states()
 
-        def one_role(role):
+        specs = {}
+
+        def prepare(role):
             in_dim = layout.OBS_DIM[role]
             self.k.es_perturb(self.theta[role], in_dim, self.sigma_dev(role), self.seed, role, self.gen,
                               self.shard.row0, self.shard.n_local, out=self.members[role])
@@ -610,20 +653,13 @@ class ESEngine(_EngineBase):
             else:
                 init = self._initial_states(self.P, 1, self.shard, ROLES.index(role) + 4 * self.gen)
             opp_a, opp_b = self._base_opponents(role)
-            if self.k1_events is not None:
-                e0 = torch.cuda.Event(enable_timing=True)
-                e1 = torch.cuda.Event(enable_timing=True)
-                e0.record()
-            out = self.k.mpe_rollout(role, self.members[role], opp_a, opp_b, init,
-                                     n_cycles=_limit_cycles(self.k, limit), pos_first=self.pos_first,
-                                     status=self.status, variant=self.variant)
-            if self.k1_events is not None:
-                e1.record()
-                self.k1_events.append((e0, e1))
-            slot = self._role_slot(out, role, limit)                  # [n_local, 1, E]
-            self.rewards[role] = slot.mean(dim=(1, 2)).contiguous()
+            specs[role] = (role, self.members[role], opp_a, opp_b, init)
 
-        self._run_roles(one_role)
+        self._run_roles(prepare)
+        outs = self._rollouts([specs[r] for r in ROLES], limit)
+        for role in ROLES:
+            slot = self._role_slot(outs[role], role, limit)           # [n_local, 1, E]
+            self.rewards[role] = slot.mean(dim=(1, 2)).contiguous()
 
     def update(self):
         """compute_weight_update + apply (evolutionary_strategy.py:120-148,255-265) for the three

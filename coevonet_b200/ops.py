@@ -156,6 +156,51 @@ def mpe_rollout(member_role, members, opp_a, opp_b, init, *, n_cycles=MAX_CYCLES
     return out
 
 
+def mpe_rollout_roles(roles, *, n_cycles=MAX_CYCLES, pos_first=True, init_shared=False, variant=0, status=None):
+    """K1 for the roles of one generation in one pass (``cev_mpe_rollout_roles_f32``).
+
+    ``roles``: list of (member_role, members fp32[P, pitch], opp_a fp32[K, pitch], opp_b, init fp64[P, K, E, 11])
+    with the same P, K, E for every role.  Returns the list of fp64 [P, K, E, 4] results, identical to one
+    :func:`mpe_rollout` per role."""
+    outs, recs, keep = [], (_lib.RolloutRole * len(roles))(), []
+    P = K = E = None
+    dev = None
+    for i, (member_role, members, opp_a, opp_b, init) in enumerate(roles):
+        dev = _need_cuda(members, opp_a, opp_b, init, status)
+        seat = layout.SEAT_OF[member_role] if isinstance(member_role, str) else int(member_role)
+        p_, k_ = members.shape[0], opp_a.shape[0]
+        e_ = init.shape[1] if init_shared else init.shape[2]
+        if opp_b.shape[0] != k_:
+            raise _lib.CevError("opp_a and opp_b must hold the same number of rows")
+        if (init_shared and (init.dim() != 3 or init.shape[0] != k_)) or \
+                (not init_shared and (init.dim() != 4 or tuple(init.shape[:2]) != (p_, k_))) or \
+                init.shape[-1] != _lib.INIT_STATE_DIM:
+            raise _lib.CevError("init must be fp64 [P, K, E, 11] (or [K, E, 11] with init_shared)")
+        if members.dtype != torch.float32 or init.dtype != torch.float64:
+            raise _lib.CevError("members must be float32 and init float64")
+        if P is None:
+            P, K, E = p_, k_, e_
+        elif (P, K, E) != (p_, k_, e_):
+            raise _lib.CevError("every role must have the same P, K, E")
+        out = torch.empty((p_, k_, e_, _lib.ROLLOUT_OUT_DIM), dtype=torch.float64, device=dev)
+        outs.append(out)
+        keep.append((members, opp_a, opp_b, init))
+        r = recs[i]
+        r.member_seat, r.reserved = seat, 0
+        r.members, r.member_pitch = members.data_ptr(), members.stride(0)
+        r.opp_a, r.opp_a_pitch = opp_a.data_ptr(), opp_a.stride(0)
+        r.opp_b, r.opp_b_pitch = opp_b.data_ptr(), opp_b.stride(0)
+        r.init, r.out = init.data_ptr(), out.data_ptr()
+    if not roles or P == 0:
+        return outs
+    cfg = RolloutCfg(int(n_cycles), int(bool(pos_first)), int(variant), 0)
+    _, n_launch = rollout_plan(dev.index, P, K, E, n_cycles, variant)
+    check(_call("cev_mpe_rollout_roles_f32", _h(dev), len(roles), recs, P, K, int(bool(init_shared)), E,
+                ctypes.byref(cfg), _ptr(status), _stream(dev), launches=n_launch * len(roles)),
+          "cev_mpe_rollout_roles_f32")
+    return outs
+
+
 def mpe_rollout_trace(member_role, members, opp_a, opp_b, init, *, n_cycles=MAX_CYCLES, pos_first=True,
                       forced_actions=None, status=None):
     """K1 lockstep kernels with parity instrumentation: returns (out fp64 [P,K,E,4], logits fp32

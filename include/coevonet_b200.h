@@ -103,6 +103,31 @@ int cev_mpe_rollout_f32(cev_handle* h, int member_seat,
                         double* out, int32_t* status, cev_stream stream);
 
 /*
+ * K1 for the roles of one generation in ONE pass (lockstep kernels): the reference evaluates the three
+ * roles one after the other (evolutionary_strategy.py:236-251; genetic_algorithm.py:125-217); here their
+ * member kernels run back to back on `stream`, their opponent kernels back to back beside them on a
+ * share of the SMs, and every role's world step waits only for that role's two kernels.  Results are
+ * identical to n_roles calls of cev_mpe_rollout_f32 with variant 3.  Every role has the same P, K, E
+ * (n_roles <= 3); a shape below the lockstep threshold is played role by role.
+ */
+typedef struct {
+    int32_t member_seat;         /* 0 adversary_0, 1 agent_0, 2 agent_1 */
+    int32_t reserved;
+    const float* members;        /* [P, member_pitch] */
+    int64_t member_pitch;
+    const float* opp_a;          /* [K, opp_a_pitch], the lower of the two other seats */
+    int64_t opp_a_pitch;
+    const float* opp_b;
+    int64_t opp_b_pitch;
+    const double* init;          /* fp64 [P,K,E,11] or [K,E,11] (init_shared) */
+    double* out;                 /* fp64 [P,K,E,4] */
+} cev_rollout_role;
+
+int cev_mpe_rollout_roles_f32(cev_handle* h, int n_roles, const cev_rollout_role* roles,
+                              int P, int K, int init_shared, int E,
+                              const cev_rollout_cfg* cfg, int32_t* status, cev_stream stream);
+
+/*
  * K1, lockstep kernels (variant 3) with parity instrumentation: the same launches as
  * cev_mpe_rollout_f32, plus -- each optional -- teacher forcing and traces, laid out
  * [n_cycles][3 seats][N = P*K*E episodes]:

@@ -206,7 +206,9 @@ def test_es_role_overlap_and_kernel_timing_do_not_change_results():
     ms, n = ops.kernel_timing_read(0, 0)
     ms_o, n_o = ops.kernel_timing_read(0, 1)
     ops.kernel_timing_enable(0, False)
-    assert n == n_o == 2 * 3 * 25 and ms > 0 and ms_o > 0      # engine b (default stream handle): 2 steps x 3 roles
+    # with the timing hook on, both engines play role by role through the default-stream handle:
+    # 2 engines x 2 steps x 3 roles x 25 world steps
+    assert n == n_o == 2 * 2 * 3 * 25 and ms > 0 and ms_o > 0
     for r in engine.ROLES:
         assert torch.equal(a.rewards[r], b.rewards[r])
         assert torch.equal(a.theta[r], b.theta[r])

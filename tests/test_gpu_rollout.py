@@ -256,3 +256,26 @@ def test_lockstep_cta_pair_form_matches_oracle():
     env = dict(os.environ, CEV_LS_PAIR="1")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("P,K,E", [(192, 1, 16), (40, 2, 9)])
+def test_roles_in_one_pass_equal_one_pass_per_role(P, K, E):
+    """cev_mpe_rollout_roles_f32 (the three roles' member / opponent kernels interleaved on three
+    streams) returns bit for bit what three cev_mpe_rollout_f32 calls with the lockstep kernels do."""
+    from coevonet_b200 import layout, ops
+    nets = _nets(max(P, K), max(P, K), max(P, K), seed=777)
+    rows = {r: _padded(nets[r], layout.OBS_DIM[r]) for r in nets}
+    specs = []
+    for i, role in enumerate(("agent_0", "agent_1", "adversary_0")):
+        ms = layout.SEAT_OF[role]
+        others = [layout.SEATS[s] for s in range(3) if s != ms]
+        init = ops.init_states(99, i, P * K * E, "cuda").reshape(P, K, E, 11)
+        specs.append((role, rows[role][:P].contiguous(), rows[others[0]][:K].contiguous(),
+                      rows[others[1]][:K].contiguous(), init))
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    fused = ops.mpe_rollout_roles(specs, variant=3, status=status)
+    torch.cuda.synchronize()
+    for spec, out in zip(specs, fused):
+        single = ops.mpe_rollout(spec[0], spec[1], spec[2], spec[3], spec[4], variant=3, status=status)
+        assert torch.equal(single, out), f"{spec[0]}: fused pass differs from the single-role pass"
+    assert int(status.item()) == 0
