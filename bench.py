@@ -54,9 +54,11 @@ def _config(n_gpus):
             "roles": 3, "cycles_per_episode": CYCLES,
             "noise": "Philox4x32-10: members materialised from the seed by K5 every generation (never stored "
                      "across generations); the update reads sigma*z back as members - theta (K6, members form)",
-            "step": "one generation: 3 x (perturb, rollout, update) + 10 eval games; the three roles' "
-                    "evaluations run on three CUDA streams, the eval games on a fourth; no host round trip "
-                    "inside a generation (sigma / reward history / status live on the device)",
+            "step": "one generation: 3 x perturb (K5), the three roles' rollouts as ONE lockstep pass "
+                    "(cev_mpe_rollout_roles_f32: per role and world step a tensor-core member kernel on a share of the "
+                    "SMs beside the tensor-core opponent kernel on the rest, then the environment step), 3 x update "
+                    "(K6) + apply, 10 eval games on a high-priority stream; no host round trip inside a generation "
+                    "(sigma / reward history / status live on the device)",
             "env_step_definition": "world step (3 agent env.step calls); agent-steps/s = 3 x value",
             "cache": "inputs larger than L2 (3 x 1024 member rows = 1.7 GB per GPU vs 126 MB L2)",
             "parallelism": f"population sharded over {n_gpus} GPU(s)"}
@@ -412,8 +414,9 @@ def run_gpu_arm(ns):
                     "k1_kernels_per_call": k1_launches, "k1_ms_per_call": k1_avg_ms, "k1_calls_timed": len(k1_ms),
                     "k1_share_of_step": sum(k1_ms) / ms_serial,
                     "serial_ms_per_step": ms_serial / roof_steps,
-                    "timing_note": "kernel durations come from a separate pass with the three roles back to back on "
-                                   "one stream; in the timed region (`value`) the roles overlap on three streams",
+                    "timing_note": "kernel durations come from a separate pass with the roles and the kernels of a world "
+                                   "step back to back on one stream, every kernel ALONE on all SMs; in the timed region "
+                                   "(`value`) the member kernel runs on a share of the SMs beside the opponent kernel",
                     "k1_algorithmic_tflops": k1_flop / (k1_avg_ms * 1e-3) / 1e12,
                     "k1_algorithmic_flop_per_call": k1_flop,
                     "fp32_peak_tflops": fp32_peak,
@@ -422,38 +425,50 @@ def run_gpu_arm(ns):
                     "fp32_peak_theoretical_tflops": fp32_theory,
                     "fp32_peak_theoretical_def": f"{n_sm} SMs x 128 FMA lanes x 2 x {sm_max:.0f} MHz"}
         if k1_variant == 3 and member_n > 0:
-            # dominant kernel: ls_member_kernel, one launch per world step; it streams every member row once
-            # per launch (algorithmic bytes = rows x D x 4, D averaged over the three roles' launches)
+            # dominant kernel: ls_member_tc_kernel, one launch per role and world step; it streams every member row
+            # once per launch (algorithmic bytes = rows x D x 4, D averaged over the three roles' launches)
             row_bytes = 4.0 * sum(layout.fc_dim(layout.OBS_DIM[r]) for r in ROLES) / 3.0
             member_us = member_ms / member_n * 1e3
             opp_us = opp_ms / max(opp_n, 1) * 1e3
             alg_bytes = n_local * row_bytes
             achieved = alg_bytes / (member_us * 1e-6) / 1e9
-            member_flop = n_local * ENVS * (2 * 274944 + 272896) / 3.0
             opp_flop = 2.0 * n_local * ENVS * 2 * 512 * 256          # fc2 of the two opponent seats
+            member_fc2_flop = n_local * ENVS * 2 * 512 * 256
             hbm_floor_us = alg_bytes / (hbm_peak * 1e9) * 1e6
-            fp32_floor_us = member_flop / (fp32_peak * 1e12) * 1e6
-            roof = {"kernel": "ls_member_kernel (K1 lockstep, member forward; one launch per world step)",
+            # tensor-pipe floor of the member kernel: 16 k-tiles x 16 tcgen05.mma per member, each occupying the
+            # pipe ~45 cycles whatever N <= 64 is (scripts/probe/mma_probe.cu), members spread over all SMs
+            mma_floor_us = -(-n_local // n_sm) * 16 * 16 * 45.0 / sm_max
+            step_ms = ms_total / ns.steps
+            # HBM bytes one generation must move: every member row once per world step (rollouts), written once
+            # (K5) and read once more (K6)
+            gen_bytes = 3 * alg_bytes * (CYCLES + 2)
+            roof = {"kernel": "ls_member_tc_kernel (K1 lockstep, member forward on tcgen05 with the member's own fc2 "
+                              "matrix as the M-side operand; one launch per role and world step)",
                     "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                     "frac": achieved / hbm_peak,
                     "floors": {
-                        "per_launch_hbm_us": hbm_floor_us, "per_launch_fp32_us": fp32_floor_us,
-                        "per_launch_fp32_theoretical_us": member_flop / (fp32_theory * 1e12) * 1e6,
+                        "per_launch_hbm_us": hbm_floor_us, "per_launch_tensor_us": mma_floor_us,
                         "per_rollout_hbm_bytes_streamed": alg_bytes * CYCLES,
                         "per_rollout_hbm_bytes_if_rows_stayed_on_chip": alg_bytes,
                         "note": "the lockstep form re-streams every member row once per world step (25x the "
                                 "once-per-rollout bytes of SURVEY.md 8d): that is a design choice, not the "
-                                "algorithm.  Per launch the HBM floor is above the FP32 floor, so `bound` is "
-                                "hbm; against the FP32 pipe the kernel is at fp32_frac.  The kernel sits "
-                                "between both floors because ~40 % of a CTA's life is outside the saturated "
-                                "fc2 loop (profiles/README.md)."},
+                                "algorithm (1.7 GB of member rows per GPU do not fit on chip).  Per launch the HBM "
+                                "floor is above the tensor-pipe floor (a tcgen05.mma with N = 32 still occupies the "
+                                "pipe ~45 cycles), so `bound` is hbm.  `frac` is the kernel ALONE on all SMs; in "
+                                "the timed region it gets a share of the SMs and the opponent kernel the rest, "
+                                "see whole_step."},
+                    "whole_step": {
+                        "hbm_bytes_per_generation": gen_bytes,
+                        "achieved_gbs": gen_bytes / (step_ms * 1e-3) / 1e9,
+                        "frac_of_hbm_peak": gen_bytes / (step_ms * 1e-3) / 1e9 / hbm_peak,
+                        "note": "all HBM traffic a generation needs (rollout streams + K5 write + K6 read) over the "
+                                "whole generation time: the rollout streams run under the opponents' MMAs"},
                     "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks_src})",
                     "us_per_launch": member_us, "launches_timed": member_n,
                     "share_of_step": member_ms / ms_serial,
                     "algorithmic_bytes_per_launch": alg_bytes,
                     "algorithmic_bytes_per_unit": row_bytes, "unit_def": "member row per world step",
-                    "fp32_tflops": member_flop / (member_us * 1e-6) / 1e12,
-                    "fp32_frac": member_flop / (member_us * 1e-6) / 1e12 / fp32_peak,
+                    "issued_tf32_tflops": 4 * member_fc2_flop / (member_us * 1e-6) / 1e12,
                     "traffic": traffic["dram_bytes_per_launch"] * n_local / traffic["members"] if traffic else None,
                     "traffic_source": traffic["source"] if traffic else None,
                     "second_kernel": {
@@ -465,7 +480,8 @@ def run_gpu_arm(ns):
                         "peak": tf32_peak, "frac": 3 * opp_flop / (opp_us * 1e-6) / 1e12 / tf32_peak,
                         "peak_source": f"half of MEASURED_PEAKS.json bf16_tflops_sustained ({peaks_src}): dense TF32 "
                                        "runs at half the bf16 rate; frac counts the 3 issued MMAs per algorithmic "
-                                       "product; 256 jobs on 148 SMs = 2 rounds at this shape (0.86 occupancy)"}}
+                                       "product; alone on 148 SMs the 256 jobs of this shape make 2 rounds (0.86 "
+                                       "occupancy), in the timed region the kernel runs on its share of the SMs"}}
         else:
             achieved = k1_flop / (k1_avg_ms * 1e-3) / 1e12
             roof = {"kernel": "rollout_cluster_kernel<16> (K1)", "bound": "fp32", "achieved": achieved,

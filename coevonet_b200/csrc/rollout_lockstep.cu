@@ -12,13 +12,12 @@
 // evolutionary_strategy.py:77/94/111; the GA Hall-of-Fame rows, genetic_algorithm.py:138-139).
 // With all episodes advanced in lockstep that work is a dense [episodes x 512] . [512 x 256]
 // GEMM and belongs on the tensor cores; only the member's own forward (unique weights per
-// member) stays on the FP32 pipe.  Per world step:
+// member) is a matrix that nobody else reads: its kernel is bound by the HBM stream of the member rows.  Per world step:
 //
-//   ls_member_kernel  one 4-warp CTA per (member, 16 episodes), two CTAs per SM: layer 1 + LayerNorm on CUDA
-//                     cores, fc2 with packed FFMA2 (8 rows x 8 envs of accumulators per lane) from 8 KB TMA
-//                     tensor tiles ([128 rows x 16 k], 64B swizzle) of the member's own row streamed from
-//                     HBM (8 slots, each warp double-buffers its own tiles, no CTA-wide barrier in the
-//                     loop), LayerNorm-2 + output layer + first-max argmax inside the CTA.
+//   ls_member_tc_kernel (ls_member_tc.cuh) persistent, job = (member, 16 episodes): the member's fc2 matrix as the
+//                     M-side operand of tcgen05 MMAs (3xTF32, both split parts in tensor memory), streamed once by
+//                     TMA; layer 1 fused through closed-form LayerNorm statistics; LayerNorm-2 + output layer +
+//                     first-max argmax in the epilogue warps.  Runs on a share of the SMs BESIDE ls_opp_kernel.
 //   ls_opp_kernel     persistent, one CTA per SM, job = (opponent seat, opponent set, 128 episodes):
 //                     8 producer warps (warp = 16-byte k chunk, lane = 4 episode rows) compute layer 1 +
 //                     LayerNorm + ReLU and write the activations, split into TF32 hi + lo parts,
@@ -33,7 +32,7 @@
 //   ls_env_step_kernel one thread per episode: fp64 physics, rewards, next observations
 //                     (bit-exact with oracle/mpe_env.py given equal actions).
 //
-// Arithmetic: member forward fp32 (FFMA); opponent fc2 3xTF32 with fp32 accumulation (error
+// Arithmetic: member and opponent fc2 3xTF32 with fp32 accumulation, layer 1 / LayerNorm / output fp32 (error
 // ~1e-6 of the activations' scale, the same order as fp32 summation-order noise); environment fp64.
 #include <stdlib.h>
 
@@ -291,383 +290,17 @@ __global__ void __launch_bounds__(512) ls_member_l1stats_kernel(const float* __r
 }
 
 // ---------------------------------------------------------------------------------------------
-// member forward (FP32 pipe)
+// shared geometry of the member / opponent kernels
 // ---------------------------------------------------------------------------------------------
-#ifndef LS_MEMBER_TC_DEFAULT
-#define LS_MEMBER_TC_DEFAULT 1                    // member forward: 1 = tensor cores beside the opponent kernel, 0 = FP32 pipe
-#endif
 #ifndef LS_GRID_OPP_DEFAULT
-#define LS_GRID_OPP_DEFAULT 0                     // 0 = one CTA per SM
+#define LS_GRID_OPP_DEFAULT 0                     // 0 = the library's split of the SMs (ls_split_sms)
 #endif
 #ifndef LS_GRID_MEM_DEFAULT
 #define LS_GRID_MEM_DEFAULT 0
 #endif
-constexpr int LS_BT = 16;                         // episodes per CTA
-constexpr int LS_MT = 128;                        // threads per member CTA (4 warps)
-constexpr int LS_MW = LS_MT / 32;
-constexpr int LS_TILE_K = 16;                     // k per tile
-constexpr int LS_TILE_ROWS = 128;
-constexpr int LS_TILE_BYTES = LS_TILE_ROWS * LS_TILE_K * 4;   // [128 rows x 16 k] fp32 = 8 KB, 64B-swizzled
-constexpr int LS_NSLOT = 8;
-constexpr int LS_TPW = (H1 / LS_TILE_K) / 2;      // 16 tiles per warp: one row half, one k half
+constexpr int LS_BT = 16;                         // episodes per member job
 constexpr int LS_TAIL_FLOATS = 2056;              // fc2.b | ln2.g | ln2.b | out.W | out.b (+3 pad), contiguous in the row
 constexpr int LS_W1A_FLOATS = H1 * IN_GOOD + 3 * H1;
-
-// Two CTAs of four warps per SM (107 KB, up to 255 registers each): every lane owns an 8 rows x 8 envs
-// accumulator tile, so a 4-k step is 16 LDS.128 for 128 FFMA2 (the 8 x 4 tile of an 8-warp CTA needed 12
-// for 64 and left the LSU pipe as busy as the FMA pipe).  While one CTA is in its latency-bound phases
-// (layer 1, LayerNorm, reductions, launch prologue) the other one keeps the FMA pipe and the HBM stream
-// busy.  The W1 block is only needed by layer 1, so ring slots 4..7 alias it.
-struct LsMemberSmem {
-    static constexpr size_t off_ring = 0;
-    static constexpr size_t off_w1a = off_ring + (size_t)(LS_NSLOT / 2) * LS_TILE_BYTES;   // = slots 4..7
-    static constexpr size_t off_h1p = off_ring + (size_t)LS_NSLOT * LS_TILE_BYTES;
-    static constexpr size_t off_tail = off_h1p + (size_t)H1 * LS_BT * 4;
-    static constexpr size_t off_obs = off_tail + (size_t)LS_TAIL_FLOATS * 4;
-    static constexpr size_t off_red1 = off_obs + (size_t)LS_BT * 12 * 4;
-    static constexpr size_t off_red = off_red1 + (size_t)2 * LS_MW * LS_BT * 4;
-    static constexpr size_t off_flag = off_red + (size_t)7 * LS_MW * LS_BT * 4;
-    static constexpr size_t off_bar = off_flag + 16;
-    static constexpr size_t total = off_bar + (size_t)(LS_NSLOT + 2) * 8 + 1024 /*alignment slack*/;
-};
-static_assert((size_t)LS_W1A_FLOATS * 4 <= (size_t)(LS_NSLOT / 2) * LS_TILE_BYTES, "W1 block must fit the aliased slots");
-static_assert(2 * (LsMemberSmem::total + 1024) <= 233472, "two member CTAs must fit one SM");
-
-struct LsMemberParams {
-    const float* members;
-    int64_t pitch;
-    int n_chunks, KE, seat;
-    int64_t N;
-    const float* obs;     // this seat's [N][12]
-    int32_t* act;         // this seat's [N]
-    float* gap;
-    int32_t* status;
-    float* logits;        // this seat's [N][5] of this cycle (parity instrumentation; null in production)
-};
-
-// Layer 1 + LayerNorm + ReLU for the CTA's BT episodes with LS_MT threads (the 128-thread form of
-// rollout_common.cuh's layer1): thread (ep = t % 8 env pair, g = t / 8) owns the row PAIRS g + 16 i;
-// output in the k-pair interleaved layout h1p[(k >> 1) * (2 BT) + 2 e + (k & 1)].
-template <int IN>
-__device__ __forceinline__ void ls_layer1(const float* __restrict__ w1a, const float* __restrict__ obs_seat,
-                                          float* __restrict__ h1p, float* __restrict__ red1, int* flag) {
-    constexpr int BT = LS_BT;
-    constexpr int NEP = BT / 2;             // env pairs
-    constexpr int G = LS_MT / NEP;          // 16 row-pair groups
-    constexpr int NP = (H1 / 2) / G;        // 16 row pairs per thread
-    constexpr int NV = 2 * IN / 4;          // float4 per row pair of fc1.W
-    const int t = threadIdx.x, ep = t % NEP, g = t / NEP, warp = t >> 5, lane = t & 31;
-    const float* fc1w = w1a;
-    const float* fc1b = w1a + H1 * IN;
-    const float* ln1g = fc1b + H1;
-    const float* ln1b = ln1g + H1;
-
-    float2 ob[2][IN / 2];
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int k = 0; k < IN / 2; ++k)
-            ob[j][k] = *reinterpret_cast<const float2*>(obs_seat + (2 * ep + j) * 12 + 2 * k);
-
-    float pre[NP][2][2];                    // [pair][row in pair][env in pair]
-    float lsum[2] = {0.f, 0.f};
-#pragma unroll
-    for (int i = 0; i < NP; ++i) {
-        const int rp = g + G * i;
-        float w[2 * IN];
-        const float4* wp = reinterpret_cast<const float4*>(fc1w + rp * 2 * IN);
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-            const float4 x = wp[v];
-            w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
-        }
-        const float2 bb = *reinterpret_cast<const float2*>(fc1b + 2 * rp);
-#pragma unroll
-        for (int r = 0; r < 2; ++r)
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int k = 0; k < IN / 2; ++k)
-                    acc = ffma2(make_float2(w[r * IN + 2 * k], w[r * IN + 2 * k + 1]), ob[j][k], acc);
-                pre[i][r][j] = (acc.x + acc.y) + (r ? bb.y : bb.x);
-                lsum[j] += pre[i][r][j];
-            }
-    }
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        lsum[j] = group_sum<NEP>(lsum[j]);
-        if (lane < NEP) red1[warp * BT + 2 * ep + j] = lsum[j];
-    }
-    __syncthreads();
-    float mean[2], lsq[2] = {0.f, 0.f};
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        float tot = 0.f;
-#pragma unroll
-        for (int w = 0; w < LS_MW; ++w) tot += red1[w * BT + 2 * ep + j];
-        mean[j] = tot * (1.0f / H1);
-    }
-#pragma unroll
-    for (int i = 0; i < NP; ++i)
-#pragma unroll
-        for (int r = 0; r < 2; ++r)
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                pre[i][r][j] -= mean[j];
-                lsq[j] = fmaf(pre[i][r][j], pre[i][r][j], lsq[j]);
-            }
-    float* red1b = red1 + LS_MW * BT;
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        lsq[j] = group_sum<NEP>(lsq[j]);
-        if (lane < NEP) red1b[warp * BT + 2 * ep + j] = lsq[j];
-    }
-    __syncthreads();
-    float rstd[2];
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        float tot = 0.f;
-#pragma unroll
-        for (int w = 0; w < LS_MW; ++w) tot += red1b[w * BT + 2 * ep + j];
-        const float var = tot * (1.0f / H1);
-        if (!isfinite(mean[j]) || !isfinite(var)) *flag = 1;
-        rstd[j] = 1.0f / sqrtf(var + LN_EPS);
-    }
-#pragma unroll
-    for (int i = 0; i < NP; ++i) {
-        const int rp = g + G * i;
-        const float2 gg = *reinterpret_cast<const float2*>(ln1g + 2 * rp);
-        const float2 be = *reinterpret_cast<const float2*>(ln1b + 2 * rp);
-        float4 o;
-        o.x = fmaxf(fmaf(pre[i][0][0] * rstd[0], gg.x, be.x), 0.f);
-        o.y = fmaxf(fmaf(pre[i][1][0] * rstd[0], gg.y, be.y), 0.f);
-        o.z = fmaxf(fmaf(pre[i][0][1] * rstd[1], gg.x, be.x), 0.f);
-        o.w = fmaxf(fmaf(pre[i][1][1] * rstd[1], gg.y, be.y), 0.f);
-        *reinterpret_cast<float4*>(h1p + rp * (2 * BT) + 4 * ep) = o;
-    }
-}
-
-// One [128 rows x 16 k] tile of fc2 for one warp: lane = (eg = lane & 1: 8 envs, rl = lane >> 1: row lane),
-// rows rl + 16 i (i < 8).  Tile rows are 64 bytes, 16-byte chunk c of row r stored at c ^ ((r >> 1) & 3)
-// (TMA SWIZZLE_64B): the 16 row lanes of a load read 256 bytes in the minimal two wavefronts.
-__device__ __forceinline__ void ls_fc2_tile(const float4* __restrict__ tile, const float* __restrict__ h1p, int kbase,
-                                            float2 (&acc)[8][8]) {
-    const int lane = threadIdx.x & 31;
-    const int eg = lane & 1, rl = lane >> 1;
-    const int sw = (rl >> 1) & 3;                 // (r >> 1) & 3 for r = rl + 16 i
-    const float4* wrow0 = tile + rl * 4;
-    const float* hbase = h1p + (kbase >> 1) * (2 * LS_BT) + eg * 16;
-#pragma unroll
-    for (int st = 0; st < LS_TILE_K / 4; ++st) {
-        // activations: two k-pairs x four env-pairs ((k even, k odd) per env)
-        float4 a[2][4];
-#pragma unroll
-        for (int kp = 0; kp < 2; ++kp)
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                a[kp][j] = *reinterpret_cast<const float4*>(hbase + (2 * st + kp) * (2 * LS_BT) + j * 4);
-        const int col = st ^ sw;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float4 w = wrow0[i * 64 + col];
-            const float2 w0 = make_float2(w.x, w.y), w1 = make_float2(w.z, w.w);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                acc[i][2 * j] = ffma2(w0, make_float2(a[0][j].x, a[0][j].y), acc[i][2 * j]);
-                acc[i][2 * j] = ffma2(w1, make_float2(a[1][j].x, a[1][j].y), acc[i][2 * j]);
-                acc[i][2 * j + 1] = ffma2(w0, make_float2(a[0][j].z, a[0][j].w), acc[i][2 * j + 1]);
-                acc[i][2 * j + 1] = ffma2(w1, make_float2(a[1][j].z, a[1][j].w), acc[i][2 * j + 1]);
-            }
-        }
-    }
-}
-
-__global__ void __launch_bounds__(LS_MT, 2)
-ls_member_kernel(const __grid_constant__ CUtensorMap map_w2, const LsMemberParams p) {
-    using L = LsMemberSmem;
-    constexpr int BT = LS_BT;
-    constexpr int G = LS_MT / BT;    // 8 row groups
-    constexpr int RP = H2 / G;       // 32 fc2 rows per thread after the k-split reduce
-    // 1024-byte alignment for the swizzled TMA tiles, computed as an OFFSET into the __shared__ array so
-    // the compiler keeps the shared address space (LDS/STS, not generic LD/ST)
-    extern __shared__ unsigned char ls_raw[];
-    unsigned char* smem = ls_raw + ((1024u - (smem_u32(ls_raw) & 1023u)) & 1023u);
-    unsigned char* ring = smem + L::off_ring;
-    float* h1p = reinterpret_cast<float*>(smem + L::off_h1p);        // activations, later the k-split partials
-    float* w1a = reinterpret_cast<float*>(smem + L::off_w1a);        // aliases ring slots 4..7
-    float* tail = reinterpret_cast<float*>(smem + L::off_tail);
-    float* obs = reinterpret_cast<float*>(smem + L::off_obs);
-    float* red1 = reinterpret_cast<float*>(smem + L::off_red1);
-    float* redA = reinterpret_cast<float*>(smem + L::off_red);       // [MW][BT]
-    float* redB = redA + LS_MW * BT;                                 // [MW][BT]
-    float* redC = redB + LS_MW * BT;                                 // [MW][5][BT]
-    int* flag = reinterpret_cast<int*>(smem + L::off_flag);
-    uint64_t* bar_tile = reinterpret_cast<uint64_t*>(smem + L::off_bar);   // [LS_NSLOT]
-    uint64_t* bar_w1 = bar_tile + LS_NSLOT;
-    uint64_t* bar_tail = bar_w1 + 1;
-
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int m = blockIdx.x / p.n_chunks, ch = blockIdx.x % p.n_chunks;
-    const int n_env = min(BT, p.KE - ch * BT);
-    const int64_t ep0 = (int64_t)m * p.KE + (int64_t)ch * BT;
-    const float* mrow = p.members + (int64_t)m * p.pitch;
-    const int in_dim = seat_in_dim(p.seat);
-    const FcOffsets om = fc_offsets(in_dim);
-
-    if (t == 0) {
-        *flag = 0;
-        for (int i = 0; i < LS_NSLOT + 2; ++i) mbar_init(bar_tile + i, 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-    // tile sequence s = i * 4 + w: the i-th tile of warp w = row half (w & 1), k-tile (w >> 1) * 16 + i;
-    // it lives in slot s % 8, so warp w double-buffers its own stream in slots w and w + 4.
-    auto issue_tile = [&](int s) {
-        const int w = s & 3, i = s >> 2, slot = s & (LS_NSLOT - 1);
-        const int kt = (w >> 1) * LS_TPW + i, rh = w & 1;
-        mbar_arrive_expect_tx(bar_tile + slot, LS_TILE_BYTES);
-        tma_load_3d(ring + (size_t)slot * LS_TILE_BYTES, &map_w2, bar_tile + slot, kt * LS_TILE_K, rh * LS_TILE_ROWS, m);
-    };
-    if (t == 0) {
-        const uint32_t w1_bytes = (uint32_t)(H1 * in_dim + 3 * H1) * 4;
-        mbar_arrive_expect_tx(bar_w1, w1_bytes);
-        bulk_g2s(w1a, mrow, w1_bytes, bar_w1);
-#pragma unroll 1
-        for (int s = 0; s < LS_NSLOT / 2; ++s) issue_tile(s);      // every warp's first tile (slots 0..3)
-        mbar_arrive_expect_tx(bar_tail, LS_TAIL_FLOATS * 4);
-        bulk_g2s(tail, mrow + om.fc2b, LS_TAIL_FLOATS * 4, bar_tail);
-    }
-    if (t < BT * 3) {
-        const int e = t / 3, v = t % 3;
-        const int64_t ep = ep0 + (e < n_env ? e : 0);
-        reinterpret_cast<float4*>(obs)[e * 3 + v] = __ldg(reinterpret_cast<const float4*>(p.obs) + ep * 3 + v);
-    }
-    __syncthreads();
-    mbar_wait(bar_w1, 0);
-    if (p.seat == 0) ls_layer1<IN_ADV>(w1a, obs, h1p, red1, flag);
-    else ls_layer1<IN_GOOD>(w1a, obs, h1p, red1, flag);
-    __syncthreads();          // h1p complete; the W1 block is dead, slots 4..7 are free
-    if (lane == 0) {
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic reads of W1 before the TMA writes
-        issue_tile(4 + warp);
-    }
-
-    // ---- fc2: warp w = (row half w & 1, k half w >> 1), 16 tiles of [128 x 16] -----------------
-    float2 acc[8][8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = make_float2(0.f, 0.f);
-#pragma unroll 1
-    for (int i = 0; i < LS_TPW; ++i) {
-        const int slot = warp + 4 * (i & 1);
-        mbar_wait(bar_tile + slot, (uint32_t)(i >> 1));
-        ls_fc2_tile(reinterpret_cast<const float4*>(ring + (size_t)slot * LS_TILE_BYTES), h1p,
-                    ((warp >> 1) * LS_TPW + i) * LS_TILE_K, acc);
-        __syncwarp();
-        if (lane == 0 && i + 2 < LS_TPW) issue_tile((i + 2) * 4 + warp);
-    }
-    __syncthreads();          // every warp is done reading h1p
-    {
-        float* part = h1p;    // [2 k-halves][256 rows][BT]
-        const int eg = lane & 1, rl = lane >> 1;
-        const int kh = warp >> 1, rh = warp & 1;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int row = rh * LS_TILE_ROWS + rl + 16 * i;
-            float* dst = part + ((size_t)(kh * H2 + row)) * BT + eg * 8;
-            float4 v0, v1;
-            v0.x = acc[i][0].x + acc[i][0].y;
-            v0.y = acc[i][1].x + acc[i][1].y;
-            v0.z = acc[i][2].x + acc[i][2].y;
-            v0.w = acc[i][3].x + acc[i][3].y;
-            v1.x = acc[i][4].x + acc[i][4].y;
-            v1.y = acc[i][5].x + acc[i][5].y;
-            v1.z = acc[i][6].x + acc[i][6].y;
-            v1.w = acc[i][7].x + acc[i][7].y;
-            *reinterpret_cast<float4*>(dst) = v0;
-            *reinterpret_cast<float4*>(dst + 4) = v1;
-        }
-    }
-    __syncthreads();
-    mbar_wait(bar_tail, 0);
-    const float* b2 = tail;
-    const float* g2 = tail + H2;
-    const float* be2 = tail + 2 * H2;
-    const float* w3 = tail + 3 * H2;
-    const float* b3 = tail + 3 * H2 + NACT * H2;
-    const int e1 = t % BT, g1 = t / BT;
-    float pre2[RP];
-    float lsum = 0.f;
-#pragma unroll
-    for (int j = 0; j < RP; ++j) {
-        const int row = g1 + G * j;
-        pre2[j] = (h1p[(size_t)row * BT + e1] + h1p[(size_t)(H2 + row) * BT + e1]) + b2[row];
-        lsum += pre2[j];
-    }
-    lsum = group_sum<BT>(lsum);
-    if (lane < BT) redA[warp * BT + e1] = lsum;
-    __syncthreads();
-    float mean = 0.f;
-#pragma unroll
-    for (int w = 0; w < LS_MW; ++w) mean += redA[w * BT + e1];
-    mean *= (1.0f / H2);
-    float lsq = 0.f;
-#pragma unroll
-    for (int j = 0; j < RP; ++j) {
-        const float d = pre2[j] - mean;
-        lsq = fmaf(d, d, lsq);
-    }
-    lsq = group_sum<BT>(lsq);
-    if (lane < BT) redB[warp * BT + e1] = lsq;
-    __syncthreads();
-    float var = 0.f;
-#pragma unroll
-    for (int w = 0; w < LS_MW; ++w) var += redB[w * BT + e1];
-    var *= (1.0f / H2);
-    if (!isfinite(mean) || !isfinite(var)) *flag = 1;
-    const float rstd = 1.0f / sqrtf(var + LN_EPS);
-    float pl[NACT] = {0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int j = 0; j < RP; ++j) {
-        const int row = g1 + G * j;
-        const float h = fmaxf(fmaf((pre2[j] - mean) * rstd, g2[row], be2[row]), 0.f);
-#pragma unroll
-        for (int a = 0; a < NACT; ++a) pl[a] = fmaf(w3[a * H2 + row], h, pl[a]);
-    }
-#pragma unroll
-    for (int a = 0; a < NACT; ++a) {
-        const float v = group_sum<BT>(pl[a]);
-        if (lane < BT) redC[(warp * NACT + a) * BT + e1] = v;
-    }
-    __syncthreads();
-    if (t < BT) {
-        float lg[NACT];
-        bool fin = true;
-#pragma unroll
-        for (int a = 0; a < NACT; ++a) {
-            float v = redC[a * BT + t];
-#pragma unroll
-            for (int w = 1; w < LS_MW; ++w) v += redC[(w * NACT + a) * BT + t];
-            lg[a] = v + b3[a];
-            fin = fin && isfinite(lg[a]);
-        }
-        if (!fin) *flag = 1;
-        float gap;
-        const int a = argmax_first5(lg, gap);
-        if (t < n_env) {
-            p.act[ep0 + t] = a;
-            p.gap[ep0 + t] = gap;
-            if (p.logits) {
-#pragma unroll
-                for (int q = 0; q < NACT; ++q) p.logits[(ep0 + t) * NACT + q] = lg[q];
-            }
-        }
-    }
-    __syncthreads();
-    if (t == 0 && *flag && p.status) atomicOr(p.status, CEV_STATUS_NONFINITE);
-}
 
 // ---------------------------------------------------------------------------------------------
 // opponent forward (tcgen05, 3xTF32)
@@ -1128,13 +761,8 @@ namespace cev {
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static int ls_member_tc_enabled() {
-    static const int v = getenv("CEV_LS_MEMBER_TC") ? atoi(getenv("CEV_LS_MEMBER_TC")) : LS_MEMBER_TC_DEFAULT;
-    return v;
-}
-
-// opponent preparation (2) [+ member layer-1 statistics] + initial states + 3 kernels per world step
-int rollout_lockstep_launches(int n_cycles) { return 3 + (ls_member_tc_enabled() ? 1 : 0) + 3 * n_cycles; }
+// opponent preparation (2) + member layer-1 statistics + initial states + 3 kernels per world step
+int rollout_lockstep_launches(int n_cycles) { return 4 + 3 * n_cycles; }
 
 // How the SMs are shared out between the two persistent kernels of a world step (tensor-core member form).
 // The opponent kernel is bound by the tensor pipe of the SMs it gets (~20 us per 128-episode job, ~15 us to get
@@ -1163,9 +791,8 @@ static void ls_split_sms(int n_sm, int opp_jobs, int mem_jobs, int* g_opp, int* 
 // Everything one role's rollout needs on the device: workspace views, tensor maps, kernel parameter blocks.
 struct LsRoleCtx {
     LsBuffers b;
-    CUtensorMap map_w2, map_b, map_wtc;
+    CUtensorMap map_b, map_wtc;
     LsEnvParams ep;
-    LsMemberParams mp;
     LsOppParams op;
     LsMemberTcParams tp;
     int env_blocks;
@@ -1176,9 +803,6 @@ struct LsRoleCtx {
 static int ls_configure(cev_handle* h) {
     static bool configured[16] = {};
     if (h->device < 16 && !configured[h->device]) {
-        CEV_CUDA(cudaFuncSetAttribute(ls_member_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)LsMemberSmem::total));
-        CEV_CUDA(cudaFuncSetAttribute(ls_member_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CEV_CUDA(cudaFuncSetAttribute(ls_opp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OP_SMEM));
         CEV_CUDA(cudaFuncSetAttribute(ls_member_tc_kernel<IN_ADV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MT_SMEM));
         CEV_CUDA(cudaFuncSetAttribute(ls_member_tc_kernel<IN_GOOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MT_SMEM));
@@ -1200,7 +824,7 @@ static int ls_reserve(cev_handle* h, size_t need) {
 
 // Launches the once-per-rollout preparation of one role on `stream` (TF32 split of the opponents' fc2, layer-1
 // statistics of the opponents and, for the tensor-core member form, of every member row) and fills the context.
-static int ls_build_role(cev_handle* h, const ClusterParams& p, void* ws, int member_tc, cudaStream_t stream, LsRoleCtx* c) {
+static int ls_build_role(cev_handle* h, const ClusterParams& p, void* ws, cudaStream_t stream, LsRoleCtx* c) {
     EncodeTiledFn encode = get_encode_fn();
     if (!encode) {
         set_error("rollout_lockstep: cuTensorMapEncodeTiled is not available from the driver");
@@ -1225,12 +849,11 @@ static int ls_build_role(cev_handle* h, const ClusterParams& p, void* ws, int me
     pp.l1stats = b.l1stats;
     ls_split_w2_kernel<<<dim3(32, 2 * p.K), 256, 0, stream>>>(pp);
     ls_l1stats_kernel<<<2 * p.K, 512, 0, stream>>>(pp);
-    if (member_tc)
-        ls_member_l1stats_kernel<<<p.P, 512, 0, stream>>>(p.members, p.member_pitch, seat_in_dim(ms), b.ml1stats);
+    ls_member_l1stats_kernel<<<p.P, 512, 0, stream>>>(p.members, p.member_pitch, seat_in_dim(ms), b.ml1stats);
 
     // ---- tensor maps ---------------------------------------------------------------------------
     const FcOffsets om = fc_offsets(seat_in_dim(ms));
-    if (member_tc) {
+    {
         cuuint64_t dims[3] = {(cuuint64_t)H1, (cuuint64_t)H2, (cuuint64_t)p.P};
         cuuint64_t strides[2] = {(cuuint64_t)H1 * 4, (cuuint64_t)p.member_pitch * 4};
         cuuint32_t box[3] = {MT_BK, H2, 1};
@@ -1240,21 +863,6 @@ static int ls_build_role(cev_handle* h, const ClusterParams& p, void* ws, int me
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             set_error("rollout_lockstep: cuTensorMapEncodeTiled(member fc2, tensor-core form) failed with %d", (int)r);
-            return CEV_ERR_CUDA;
-        }
-    } else {
-        cuuint64_t dims[3] = {(cuuint64_t)H1, (cuuint64_t)H2, (cuuint64_t)p.P};
-        cuuint64_t strides[2] = {(cuuint64_t)H1 * 4, (cuuint64_t)p.member_pitch * 4};
-        cuuint32_t box[3] = {LS_TILE_K, LS_TILE_ROWS, 1};
-        cuuint32_t estr[3] = {1, 1, 1};
-        static const int l2p = getenv("CEV_LS_L2P") ? atoi(getenv("CEV_LS_L2P")) : 128;
-        CUresult r = encode(&c->map_w2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.members + om.fc2w), dims,
-                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
-                            l2p == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
-                                       : (l2p == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B),
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) {
-            set_error("rollout_lockstep: cuTensorMapEncodeTiled(member fc2) failed with %d", (int)r);
             return CEV_ERR_CUDA;
         }
     }
@@ -1285,19 +893,9 @@ static int ls_build_role(cev_handle* h, const ClusterParams& p, void* ws, int me
     ep.out = p.out;
     c->env_blocks = (int)((N + 255) / 256);
 
-    LsMemberParams& mp = c->mp;
-    mp = LsMemberParams{};
-    mp.members = p.members;
-    mp.pitch = p.member_pitch;
-    mp.KE = p.K * p.E;
-    mp.n_chunks = (mp.KE + LS_BT - 1) / LS_BT;
-    mp.seat = ms;
-    mp.N = N;
-    mp.obs = b.obs + (int64_t)ms * N * LS_OBS_PAD;
-    mp.act = b.act + (int64_t)ms * N;
-    mp.gap = b.gap + (int64_t)ms * N;
-    mp.status = p.status;
-    c->member_ctas = (int64_t)p.P * mp.n_chunks;
+    const int KE = p.K * p.E;
+    const int n_chunks = (KE + LS_BT - 1) / LS_BT;
+    c->member_ctas = (int64_t)p.P * n_chunks;
     CEV_REQUIRE(c->member_ctas < (1ll << 31), "rollout_lockstep: too many member tiles");
 
     LsOppParams& op = c->op;
@@ -1323,14 +921,14 @@ static int ls_build_role(cev_handle* h, const ClusterParams& p, void* ws, int me
     tp = LsMemberTcParams{};
     tp.members = p.members;
     tp.pitch = p.member_pitch;
-    tp.KE = mp.KE;
-    tp.n_chunks = mp.n_chunks;
+    tp.KE = KE;
+    tp.n_chunks = n_chunks;
     tp.seat = ms;
     tp.n_jobs = (int)c->member_ctas;
     tp.N = N;
-    tp.obs = mp.obs;
-    tp.act = mp.act;
-    tp.gap = mp.gap;
+    tp.obs = b.obs + (int64_t)ms * N * LS_OBS_PAD;
+    tp.act = b.act + (int64_t)ms * N;
+    tp.gap = b.gap + (int64_t)ms * N;
     tp.l1stats = b.ml1stats;
     tp.status = p.status;
     return CEV_OK;
@@ -1348,26 +946,23 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
     if (rc) return rc;
     rc = ls_configure(h);
     if (rc) return rc;
-    const int member_tc = ls_member_tc_enabled();
     LsRoleCtx ctx;
-    rc = ls_build_role(h, p, h->ls_workspace, member_tc, stream, &ctx);
+    rc = ls_build_role(h, p, h->ls_workspace, stream, &ctx);
     if (rc) return rc;
     LsEnvParams& ep = ctx.ep;
-    LsMemberParams& mp = ctx.mp;
     LsOppParams& op = ctx.op;
     LsMemberTcParams& tp = ctx.tp;
     const int ms = ctx.ms;
     const int env_blocks = ctx.env_blocks;
-    const int64_t member_ctas = ctx.member_ctas;
     int opp_grid = op.n_jobs < h->n_sm ? op.n_jobs : h->n_sm;
     int mem_grid = tp.n_jobs < h->n_sm ? tp.n_jobs : h->n_sm;
-    static const int want_fork = getenv("CEV_LS_FORK") ? atoi(getenv("CEV_LS_FORK")) : (member_tc ? 1 : 0);
-    // The two forwards of a world step are independent (same observations).  FP32 member form: two streams let the
-    // block scheduler fill one kernel's tail with the other's CTAs (+4 % at 1024 members, -3 % at 4096: opt-in).
-    // Tensor-core member form: both kernels are persistent and get a share of the SMs each, so the HBM stream of the
-    // member rows runs under the opponents' MMAs (default).
+    // The two forwards of a world step are independent (same observations): both kernels are persistent and get a
+    // share of the SMs each (the opponent kernel on a side stream), so the HBM stream of the member rows runs under
+    // the opponents' MMAs.  With the per-kernel timing hook on (cev_kernel_timing_enable) or CEV_LS_FORK=0 they run
+    // one after the other on all SMs.
+    static const int want_fork = getenv("CEV_LS_FORK") ? atoi(getenv("CEV_LS_FORK")) : 1;
     const bool fork = want_fork && !h->timing_on;
-    if (member_tc && fork) {
+    if (fork) {
         // CEV_LS_GRID_OPP / CEV_LS_GRID_MEM override the split (development aid)
         static const int g_opp_env = getenv("CEV_LS_GRID_OPP") ? atoi(getenv("CEV_LS_GRID_OPP")) : LS_GRID_OPP_DEFAULT;
         static const int g_mem_env = getenv("CEV_LS_GRID_MEM") ? atoi(getenv("CEV_LS_GRID_MEM")) : LS_GRID_MEM_DEFAULT;
@@ -1379,18 +974,9 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
         if (g_mem < mem_grid) mem_grid = g_mem;
     }
 
-    // development aids: CEV_LS_SKIP bit 0 = no opponent kernel, bit 1 = no member kernel (timing only,
-    // results are then invalid); CEV_LS_FORK=1 = opponent kernel on a side stream beside the member kernel
+    // development aid: CEV_LS_SKIP bit 0 = no opponent kernel, bit 1 = no member kernel (timing only, results are
+    // then invalid)
     static const int skip = getenv("CEV_LS_SKIP") ? atoi(getenv("CEV_LS_SKIP")) : 0;
-    // CEV_LS_MEMBER_PAD = extra dynamic shared memory (bytes) per member CTA: 16384 leaves room for ONE member CTA
-    // per SM (timing experiment: what a member CTA delivers when it does not share the SM with a second one)
-    static const int member_pad = getenv("CEV_LS_MEMBER_PAD") ? atoi(getenv("CEV_LS_MEMBER_PAD")) : 0;
-    static bool pad_configured = false;
-    if (member_pad > 0 && !pad_configured) {
-        CEV_CUDA(cudaFuncSetAttribute(ls_member_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)LsMemberSmem::total + member_pad));
-        pad_configured = true;
-    }
     if (fork && !h->side_stream) {
         CEV_CUDA(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
         CEV_CUDA(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
@@ -1401,8 +987,7 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
     for (int c = 0; c < p.n_cycles; ++c) {
         if (p.trace_logits) {
             op.logits = p.trace_logits + (size_t)c * 3 * N * NACT;
-            mp.logits = op.logits + (size_t)ms * N * NACT;
-            tp.logits = mp.logits;
+            tp.logits = op.logits + (size_t)ms * N * NACT;
         }
         ep.forced = p.trace_forced ? p.trace_forced + (size_t)c * 3 * N : nullptr;
         ep.act_out = p.trace_actions ? p.trace_actions + (size_t)c * 3 * N : nullptr;
@@ -1427,11 +1012,7 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
         }
         if (!(skip & 2)) {
             tick(0, 0);
-            if (member_tc) {
-                ls_launch_member_tc(ctx, mem_grid, stream);
-            } else {
-                ls_member_kernel<<<(unsigned)member_ctas, LS_MT, LsMemberSmem::total + member_pad, stream>>>(ctx.map_w2, mp);
-            }
+            ls_launch_member_tc(ctx, mem_grid, stream);
             tick(0, 1);
         }
         if (fork && !(skip & 1)) CEV_CUDA(cudaStreamWaitEvent(stream, h->join_ev, 0));
@@ -1453,9 +1034,8 @@ int launch_rollout_lockstep_roles(cev_handle* h, const ClusterParams* ps, int n_
     if (n_roles <= 0) return CEV_OK;
     const ClusterParams& p0 = ps[0];
     if (p0.P <= 0 || p0.K <= 0 || p0.E <= 0) return CEV_OK;
-    const int member_tc = ls_member_tc_enabled();
     static const int want_roles = getenv("CEV_LS_ROLES") ? atoi(getenv("CEV_LS_ROLES")) : 1;
-    if (!member_tc || h->timing_on || !want_roles || n_roles > CEV_MAX_ROLES) {
+    if (h->timing_on || !want_roles || n_roles > CEV_MAX_ROLES) {
         for (int r = 0; r < n_roles; ++r) {
             const int rc = launch_rollout_lockstep(h, ps[r], stream);
             if (rc) return rc;
@@ -1491,7 +1071,7 @@ int launch_rollout_lockstep_roles(cev_handle* h, const ClusterParams* ps, int n_
     }
     LsRoleCtx ctx[CEV_MAX_ROLES];
     for (int r = 0; r < n_roles; ++r) {
-        rc = ls_build_role(h, ps[r], static_cast<char*>(h->ls_workspace) + per_role * r, 1, stream, &ctx[r]);
+        rc = ls_build_role(h, ps[r], static_cast<char*>(h->ls_workspace) + per_role * r, stream, &ctx[r]);
         if (rc) return rc;
         ctx[r].ep.last = ps[r].n_cycles == 0;
         ls_init_kernel<<<ctx[r].env_blocks, 256, 0, stream>>>(ctx[r].ep);

@@ -1,5 +1,4 @@
-run() { echo -n "== $*: "; env "$@" timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-secondary 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['value']/1e6, d['ms_per_step'])"; }
-run CEV_LS_ALT=1
-run CEV_LS_GRID_OPP=43 CEV_LS_GRID_MEM=103
-timeout 300 python scripts/ab_step.py 2>&1 | tail -12
-timeout 300 python scripts/step_breakdown.py 2>&1 | tail -12
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/r2c_pytest_all.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r2c_pytest_all.log
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-secondary 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['value']/1e6, d['ms_per_step'])"

@@ -56,7 +56,9 @@ def test_round2_line_carries_parity_secondary_and_floors():
     p = d["parity"]
     assert p["members_sampled"] >= 3 * 128 and 0.0 <= p["member_match_frac"] <= 1.0 and p["episode_forks"] >= 0
     fl = d["roofline"]["floors"]
-    assert fl["per_launch_hbm_us"] > fl["per_launch_fp32_us"] > 0           # `bound` hbm is the binding floor
+    assert fl["per_launch_hbm_us"] > fl["per_launch_tensor_us"] > 0         # `bound` hbm is the binding floor
+    ws = d["roofline"]["whole_step"]
+    assert 0.0 < ws["frac_of_hbm_peak"] < 1.0 and "ls_member_tc_kernel" in d["roofline"]["kernel"]
     assert abs(fl["per_rollout_hbm_bytes_streamed"] - 25 * fl["per_rollout_hbm_bytes_if_rows_stayed_on_chip"]) < 1
     assert d["roofline"]["fp32_peak_theoretical_tflops"] >= d["roofline"]["fp32_peak_tflops"] * 0.95
     assert d["e2e"]["steps"] == d["steps"]                                 # e2e over the full --steps, host clock
