@@ -74,6 +74,9 @@ def parse_arguments(argv=None):
                    help="GA extension (the reference has no crossover, README.md:47 vs code): probability that a "
                         "child is a uniform crossover of two elites before it is mutated; 0 = reference behaviour")
     p.add_argument("--no_plots", action="store_true")
+    p.add_argument("--no_fused_roles", action="store_true",
+                   help="play the three roles' evaluation loops as one K1 pass per role on three CUDA streams instead of "
+                        "the roles of a generation in one pass (cev_mpe_rollout_roles_f32); same results")
     p.add_argument("--resume", action="store_true",
                    help="continue from <output_dir>/engine_state_rank<r>.pt (written next to the reference-format "
                         ".pth files when --save is set): populations / base rows, HoF ring, sigmas, reward history, "
@@ -135,6 +138,7 @@ class Args:
         self.play_discarded_hof_games = a.play_discarded_hof_games
         self.update_from_members = not a.regenerate_noise
         self.plots = not a.no_plots
+        self.fused_roles = not a.no_fused_roles
         self.resume = a.resume
         self.crossover_rate = a.crossover_rate
         self.log_member_weight_stats = a.log_member_weight_stats
