@@ -78,15 +78,6 @@ struct ConvParams {
     float* y_out;                // [n_frames][positions][COUT]
 };
 
-__device__ __forceinline__ void cv_umma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                        uint32_t accumulate) {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
 template <int LAYER, int CIN_>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 deepqn_conv_tc_kernel(const __grid_constant__ CUtensorMap map_w, const ConvParams p) {
@@ -333,6 +324,7 @@ deepqn_conv_tc_kernel(const __grid_constant__ CUtensorMap map_w, const ConvParam
         }
     } else {
         // ===================== MMA issuer =====================
+        const uint32_t stage_base = tc_smem_u32(stage_mem);
         uint32_t it = 0, pass = 0;
         for (int64_t f = blockIdx.x; f < p.n_frames; f += gridDim.x)
             for (int rt = 0; rt < NRT; ++rt, ++pass) {
@@ -344,21 +336,15 @@ deepqn_conv_tc_kernel(const __grid_constant__ CUtensorMap map_w, const ConvParam
                     const uint32_t st = it % CV_STAGES, use = it / CV_STAGES;
                     tc_mbar_wait(bar_full + st, use & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                    if (lane == 0) {
-                        const uint32_t s_addr = tc_smem_u32(stage_mem + (size_t)st * S::STAGE_BYTES);
-                        const uint64_t a_hi = umma_desc_sw128(s_addr);
-                        const uint64_t a_lo = umma_desc_sw128(s_addr + CV_A_BYTES);
-                        const uint64_t b_hi = umma_desc_sw128(s_addr + 2 * CV_A_BYTES);
-                        const uint64_t b_lo = umma_desc_sw128(s_addr + 2 * CV_A_BYTES + S::B_BYTES);
-#pragma unroll
-                        for (int k8 = 0; k8 < CV_BK / 8; ++k8) {
-                            const uint64_t ko = (uint64_t)(k8 * 2);
-                            cv_umma(d_tmem, a_lo + ko, b_hi + ko, IDESC, (kt | k8) ? 1u : 0u);
-                            cv_umma(d_tmem, a_hi + ko, b_lo + ko, IDESC, 1u);
-                            cv_umma(d_tmem, a_hi + ko, b_hi + ko, IDESC, 1u);
-                        }
-                        umma_commit(bar_empty + st);
-                        if (kt == NKT - 1) umma_commit(bar_tfull + as);
+                    {
+                        // issued by one elected lane of the converged warp (tc_issue_ktile_3xtf32): with N = 32 / 64 an
+                        // MMA occupies the tensor pipe ~45 cycles, a divergent `if (lane == 0)` issue costs ~130
+                        const uint32_t s_addr = stage_base + st * S::STAGE_BYTES;
+                        tc_issue_ktile_3xtf32(d_tmem, umma_desc_sw128(s_addr), umma_desc_sw128(s_addr + CV_A_BYTES),
+                                              umma_desc_sw128(s_addr + 2 * CV_A_BYTES),
+                                              umma_desc_sw128(s_addr + 2 * CV_A_BYTES + S::B_BYTES), IDESC, kt ? 1u : 0u,
+                                              tc_smem_u32(bar_empty + st));
+                        if (kt == NKT - 1) tc_commit_elected(tc_smem_u32(bar_tfull + as));
                     }
                     __syncwarp();
                 }

@@ -92,13 +92,6 @@ __device__ __forceinline__ void mt_issue_ktile(uint32_t d_tmem, uint32_t a_tmem,
         "r"(a_tmem), "l"(x_hilo), "r"(accumulate), "r"(bar_op), "r"(MT_IDESC32)
         : "memory");
 }
-__device__ __forceinline__ void mt_commit_elected(uint32_t bar) {
-    asm volatile(
-        "{\n.reg .pred pe;\nelect.sync _|pe, 0xffffffff;\n"
-        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(bar)
-        : "memory");
-}
-
 struct LsMemberTcParams {
     const float* members;
     int64_t pitch;
@@ -215,7 +208,7 @@ ls_member_tc_kernel(const __grid_constant__ CUtensorMap map_w, const LsMemberTcP
                 tc_mbar_wait(bar_lo_full + ls, luse & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 mt_issue_ktile(d_tmem, a_tmem, x_hilo, kt ? 1u : 0u, tc_smem_u32(bar_lo_empty + ls));
-                if (kt == MT_KT - 1) mt_commit_elected(tc_smem_u32(bar_tfull + as));
+                if (kt == MT_KT - 1) tc_commit_elected(tc_smem_u32(bar_tfull + as));
                 __syncwarp();
             }
         }

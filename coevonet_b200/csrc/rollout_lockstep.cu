@@ -344,47 +344,6 @@ __device__ __forceinline__ void op_umma(uint32_t d_tmem, uint64_t a_desc, uint64
         : "memory");
 }
 
-// The twelve MMAs of one k-tile (4 k-steps x {a_lo . b_hi, a_hi . b_lo, a_hi . b_hi}, small terms first) and the commit
-// that releases the stage, issued by ONE elected lane of a CONVERGED warp: inside a divergent `if (lane == 0)` every
-// tcgen05.mma costs an ELECT + R2UR.BROADCAST chain (~20 instructions, ~130 cycles of issue for 128 cycles of tensor
-// pipe), which held the tensor pipe at ~50 %.
-__device__ __forceinline__ void op_issue_ktile(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
-                                               uint32_t accumulate, uint32_t bar_empty) {
-    asm volatile(
-        "{\n"
-        ".reg .pred pe, pa, pt;\n"
-        ".reg .b64 ah1, ah2, ah3, al1, al2, al3, bh1, bh2, bh3, bl1, bl2, bl3;\n"
-        "elect.sync _|pe, 0xffffffff;\n"
-        "setp.ne.b32 pa, %5, 0;\n"
-        "setp.eq.b32 pt, 0, 0;\n"
-        "add.s64 ah1, %1, 2;\n add.s64 ah2, %1, 4;\n add.s64 ah3, %1, 6;\n"
-        "add.s64 al1, %2, 2;\n add.s64 al2, %2, 4;\n add.s64 al3, %2, 6;\n"
-        "add.s64 bh1, %3, 2;\n add.s64 bh2, %3, 4;\n add.s64 bh3, %3, 6;\n"
-        "add.s64 bl1, %4, 2;\n add.s64 bl2, %4, 4;\n add.s64 bl3, %4, 6;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %2, %3, %7, pa;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %4, %7, pt;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %3, %7, pt;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], al1, bh1, %7, pt;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], ah1, bl1, %7, pt;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], ah1, bh1, %7, pt;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], al2, bh2, %7, pt;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], ah2, bl2, %7, pt;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], ah2, bh2, %7, pt;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], al3, bh3, %7, pt;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], ah3, bl3, %7, pt;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], ah3, bh3, %7, pt;\n"
-        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n"
-        "}\n" ::"r"(d_tmem),
-        "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(accumulate), "r"(bar_empty), "r"(OP_IDESC)
-        : "memory");
-}
-__device__ __forceinline__ void op_commit_elected(uint32_t bar) {
-    asm volatile(
-        "{\n.reg .pred pe;\nelect.sync _|pe, 0xffffffff;\n"
-        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(bar)
-        : "memory");
-}
-
 // One producer thread's share of an A tile: 16-byte chunk c (4 activations) of k-tile kt for its FOUR
 // episode rows lane + 32 j: relu(LN1(W1 x + b1)), split into TF32 hi + lo and stored K-major with the
 // 128-byte swizzle the UMMA descriptor expects (chunk c of row r at c ^ (r & 7)).  The weight loads are
@@ -733,13 +692,13 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
                 tc_mbar_wait(bar_full + st, use & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 {
-                    // issued by one elected lane of the converged warp (see op_issue_ktile)
+                    // issued by one elected lane of the converged warp (tc_issue_ktile_3xtf32, tc_common.cuh)
                     const uint32_t s_addr = stage_base + st * Geo::STAGE_BYTES;
-                    op_issue_ktile(d_tmem, umma_desc_sw128(s_addr), umma_desc_sw128(s_addr + OP_A_BYTES),
-                                   umma_desc_sw128(s_addr + 2 * OP_A_BYTES),
-                                   umma_desc_sw128(s_addr + 2 * OP_A_BYTES + Geo::B_BYTES), kt ? 1u : 0u,
-                                   tc_smem_u32(bar_empty + st));
-                    if (kt == OP_KT - 1) op_commit_elected(tc_smem_u32(bar_tfull + as));
+                    tc_issue_ktile_3xtf32(d_tmem, umma_desc_sw128(s_addr), umma_desc_sw128(s_addr + OP_A_BYTES),
+                                          umma_desc_sw128(s_addr + 2 * OP_A_BYTES),
+                                          umma_desc_sw128(s_addr + 2 * OP_A_BYTES + Geo::B_BYTES), OP_IDESC, kt ? 1u : 0u,
+                                          tc_smem_u32(bar_empty + st));
+                    if (kt == OP_KT - 1) tc_commit_elected(tc_smem_u32(bar_tfull + as));
                 }
                 __syncwarp();
             }

@@ -124,6 +124,47 @@ __device__ __forceinline__ void f3_tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) 
 }
 __device__ __forceinline__ float f3_lo(float w) { return w - __uint_as_float(__float_as_uint(w) & 0xffffe000u); }
 
+// The twelve MMAs of one k-tile (4 k-steps x {a_lo . b_hi, a_hi . b_lo, a_hi . b_hi}, small terms first) and the commit
+// that releases the stage, issued by ONE elected lane of a CONVERGED warp: inside a divergent `if (lane == 0)` every
+// tcgen05.mma costs an ELECT + R2UR.BROADCAST chain (~20 instructions, ~130 cycles of issue for 128 cycles of tensor
+// pipe), which held the tensor pipe at ~50 %.
+__device__ __forceinline__ void tc_issue_ktile_3xtf32(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                                      uint32_t idesc, uint32_t accumulate, uint32_t bar_empty) {
+    asm volatile(
+        "{\n"
+        ".reg .pred pe, pa, pt;\n"
+        ".reg .b64 ah1, ah2, ah3, al1, al2, al3, bh1, bh2, bh3, bl1, bl2, bl3;\n"
+        "elect.sync _|pe, 0xffffffff;\n"
+        "setp.ne.b32 pa, %5, 0;\n"
+        "setp.eq.b32 pt, 0, 0;\n"
+        "add.s64 ah1, %1, 2;\n add.s64 ah2, %1, 4;\n add.s64 ah3, %1, 6;\n"
+        "add.s64 al1, %2, 2;\n add.s64 al2, %2, 4;\n add.s64 al3, %2, 6;\n"
+        "add.s64 bh1, %3, 2;\n add.s64 bh2, %3, 4;\n add.s64 bh3, %3, 6;\n"
+        "add.s64 bl1, %4, 2;\n add.s64 bl2, %4, 4;\n add.s64 bl3, %4, 6;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %2, %3, %7, pa;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %4, %7, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %3, %7, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], al1, bh1, %7, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], ah1, bl1, %7, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], ah1, bh1, %7, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], al2, bh2, %7, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], ah2, bl2, %7, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], ah2, bh2, %7, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], al3, bh3, %7, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], ah3, bl3, %7, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], ah3, bh3, %7, pt;\n"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(accumulate), "r"(bar_empty), "r"(idesc)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_elected(uint32_t bar) {
+    asm volatile(
+        "{\n.reg .pred pe;\nelect.sync _|pe, 0xffffffff;\n"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(bar)
+        : "memory");
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
