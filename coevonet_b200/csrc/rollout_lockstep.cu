@@ -1047,6 +1047,7 @@ int launch_rollout_lockstep_roles(cev_handle* h, const ClusterParams* ps, int n_
     // Consecutive kernels of one kind alternate between two streams, so the next role's CTAs move in as the previous
     // role's CTAs retire (no idle tail at the end of every kernel, launch latency hidden).
     static const int alt = getenv("CEV_LS_ALT") ? atoi(getenv("CEV_LS_ALT")) : 1;
+    static const int skip = getenv("CEV_LS_SKIP") ? atoi(getenv("CEV_LS_SKIP")) : 0;   // development aid, see the single-role path
     cudaStream_t s_mem[2] = {stream, alt ? h->mem_stream2 : stream};
     cudaStream_t s_opp[2] = {h->opp_stream2[0], alt ? h->opp_stream2[1] : h->opp_stream2[0]};
     cudaStream_t s_env = h->env_stream;
@@ -1064,9 +1065,9 @@ int launch_rollout_lockstep_roles(cev_handle* h, const ClusterParams* ps, int n_
                 CEV_CUDA(cudaStreamWaitEvent(so, h->ev_env[r], 0));
                 CEV_CUDA(cudaStreamWaitEvent(sm, h->ev_env[r], 0));
             }
-            ls_opp_kernel<<<opp_grid, OP_THREADS, OP_SMEM, so>>>(ctx[r].map_b, ctx[r].op);
+            if (!(skip & 1)) ls_opp_kernel<<<opp_grid, OP_THREADS, OP_SMEM, so>>>(ctx[r].map_b, ctx[r].op);
             CEV_CUDA(cudaEventRecord(h->ev_opp[r], so));
-            ls_launch_member_tc(ctx[r], mem_grid, sm);
+            if (!(skip & 2)) ls_launch_member_tc(ctx[r], mem_grid, sm);
             CEV_CUDA(cudaEventRecord(h->ev_mem[r], sm));
             CEV_CUDA(cudaStreamWaitEvent(s_env, h->ev_opp[r], 0));
             CEV_CUDA(cudaStreamWaitEvent(s_env, h->ev_mem[r], 0));

@@ -12,7 +12,7 @@ Follows, for a batch of independent episodes:
 
 The network runs in fp32 (NumPy), the environment in fp64, like the reference.
 Pinned against the reference's own ``play_game`` by ``oracle/make_golden.py``
-/ ``tests/test_oracle_vs_reference.py``.
+/ ``tests/test_oracle_golden.py`` (the reference-generated fixtures under ``tests/golden/``).
 """
 from __future__ import annotations
 
