@@ -248,7 +248,7 @@ __device__ __forceinline__ void ls_l1stats_row(const float* __restrict__ row, in
     const int d = in + 1;
     const float* w1 = row;
     const float* b1 = row + H1 * in;
-    __shared__ float cols[11][H1];          // [W1 | b1] transposed: column a of all 512 rows
+    __shared__ float cols[11][H1 + 1];      // [W1 | b1] transposed: column a of all 512 rows (+1: conflict-free transpose)
     __shared__ double wbar[11];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     for (int i = t; i < H1 * in; i += 512) cols[i % in][i / in] = w1[i];
@@ -264,8 +264,15 @@ __device__ __forceinline__ void ls_l1stats_row(const float* __restrict__ row, in
     }
     __syncthreads();
     if (t < 11) out[t] = wbar[t];
-    for (int pr = warp; pr < 121; pr += 16) {
-        const int a = pr / 11, b = pr % 11;
+    // C is symmetric: the 66 pairs a <= b are summed (in the row order r = lane, lane + 32, ... of the full form, so
+    // C[a][b] keeps its bits) and mirrored
+    for (int pr = warp; pr < 66; pr += 16) {
+        int a = 0, rem = pr;
+        while (rem >= 11 - a) {
+            rem -= 11 - a;
+            ++a;
+        }
+        const int b = a + rem;
         double s = 0.0;
         if (a < d && b < d) {
             const double ma = wbar[a], mb = wbar[b];
@@ -273,7 +280,10 @@ __device__ __forceinline__ void ls_l1stats_row(const float* __restrict__ row, in
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) out[11 + pr] = s / H1;
+        if (lane == 0) {
+            out[11 + a * 11 + b] = s / H1;
+            out[11 + b * 11 + a] = s / H1;
+        }
     }
 }
 
@@ -1018,10 +1028,12 @@ int launch_rollout_lockstep_roles(cev_handle* h, const ClusterParams* ps, int n_
         int lo = 0, hi = 0;
         CEV_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         const int mid = hi < lo ? lo - 1 : lo;
+        static const int prio = getenv("CEV_LS_PRIO") ? atoi(getenv("CEV_LS_PRIO")) : 0;   // development aid
+        const int p_opp = prio == 1 ? lo : mid, p_mem = prio == 2 ? (hi < lo - 1 ? lo - 2 : lo) : lo;
         CEV_CUDA(cudaStreamCreateWithPriority(&h->env_stream, cudaStreamNonBlocking, hi));
-        CEV_CUDA(cudaStreamCreateWithPriority(&h->opp_stream2[0], cudaStreamNonBlocking, mid));
-        CEV_CUDA(cudaStreamCreateWithPriority(&h->opp_stream2[1], cudaStreamNonBlocking, mid));
-        CEV_CUDA(cudaStreamCreateWithPriority(&h->mem_stream2, cudaStreamNonBlocking, lo));
+        CEV_CUDA(cudaStreamCreateWithPriority(&h->opp_stream2[0], cudaStreamNonBlocking, p_opp));
+        CEV_CUDA(cudaStreamCreateWithPriority(&h->opp_stream2[1], cudaStreamNonBlocking, p_opp));
+        CEV_CUDA(cudaStreamCreateWithPriority(&h->mem_stream2, cudaStreamNonBlocking, p_mem));
         for (int r = 0; r < CEV_MAX_ROLES; ++r) {
             CEV_CUDA(cudaEventCreateWithFlags(&h->ev_opp[r], cudaEventDisableTiming));
             CEV_CUDA(cudaEventCreateWithFlags(&h->ev_mem[r], cudaEventDisableTiming));
