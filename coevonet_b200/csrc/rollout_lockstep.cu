@@ -36,6 +36,8 @@
 // ~1e-6 of the activations' scale, the same order as fp32 summation-order noise); environment fp64.
 #include <stdlib.h>
 
+#include <cuda_fp16.h>
+
 #include "rollout_common.cuh"
 #include "tc_common.cuh"
 
@@ -56,7 +58,9 @@ struct LsBuffers {
     float* obs;        // [3][N][12]
     int32_t* act;      // [3][N]
     float* gap;        // [3][N]
-    float* w2split;    // [2 seats][K][hi, lo][256][512]
+    __half* w2split;   // [2 seats][K][hi, lo][256][512] fp16, scaled by 2^s_w
+    uint32_t* wmax;    // [2 seats][K] bit pattern of max |fc2.W|
+    float* oscale;     // [2 seats][K][2]: 2^s_x (activation scale), 2^-(s_w + s_x) (accumulator unscale)
     double* l1stats;   // [2 seats][K][132]
     double* ml1stats;  // [P][132]  the members' own layer-1 statistics (tensor-core member form)
 };
@@ -72,7 +76,9 @@ static size_t ls_carve(void* base, int64_t N, int K, int P, LsBuffers* b) {
         return r;
     };
     LsBuffers t;
-    t.w2split = static_cast<float*>(take((size_t)2 * K * 2 * H2 * H1 * sizeof(float)));
+    t.w2split = static_cast<__half*>(take((size_t)2 * K * 2 * H2 * H1 * sizeof(__half)));
+    t.wmax = static_cast<uint32_t*>(take((size_t)2 * K * sizeof(uint32_t)));
+    t.oscale = static_cast<float*>(take((size_t)2 * K * 2 * sizeof(float)));
     t.st = static_cast<double*>(take((size_t)LS_ST_FIELDS * N * sizeof(double)));
     t.acc = static_cast<double*>(take((size_t)3 * N * sizeof(double)));
     t.min_gap = static_cast<float*>(take((size_t)N * sizeof(float)));
@@ -206,38 +212,70 @@ __global__ void __launch_bounds__(256) ls_env_step_kernel(const LsEnvParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// opponent preparation (once per launch): TF32 hi/lo split of fc2.W, layer-1 row statistics
+// opponent preparation (once per launch): scaled FP16 hi/lo split of fc2.W, layer-1 row statistics
+//
+// The opponents' fc2 runs as THREE kind::f16 MMAs per product, x1.w1 + x2.w1 + x1.w2 with v1 = fp16(v'),
+// v2 = fp16(v' - v1) of the power-of-two scaled operands v' = 2^s v ("2xFP16": 22-23 significand bits per
+// operand, the same as the TF32 hi/lo split of rounds 1-2, at twice the tensor rate and half the operand
+// bytes).  FP16 has five exponent bits, so the scales keep both parts in the normal range:
+//   s_w = 14 - ilogb(max |fc2.W|)            (|w'| < 2^15; the residuals sit 2^-12 below, still normal)
+//   s_x = 13 - ilogb(22.63 max|ln1.g| + max|ln1.b|)   (a LayerNorm output over 512 values is at most sqrt(511))
+// and the epilogue multiplies the fp32 accumulator by 2^-(s_w + s_x).  Values that would be subnormal after
+// scaling lose RELATIVE precision only where they are 2^-24 of the largest weight: an absolute error of
+// 2^-25 2^-s per element, far below fp32 summation noise of the dot product.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float tf32_rna(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
-
 struct LsPrepParams {
     const float* opp[2];
     int64_t opp_pitch[2];
     int seat[2];
     int K;
-    float* w2split;
+    __half* w2split;
+    uint32_t* wmax;
+    float* oscale;
     double* l1stats;
 };
+
+__device__ __forceinline__ int ls_scale_exp(float bound, int target) {
+    // 2^s * bound < 2^(target + 1); clamped so that 2^s and its inverse stay far from fp32's range limits
+    if (!(bound > 0.f) || !isfinite(bound)) return 0;
+    const int s = target - ilogbf(bound);
+    return s < -40 ? -40 : (s > 40 ? 40 : s);
+}
+
+__global__ void __launch_bounds__(256) ls_wmax_kernel(const LsPrepParams p) {
+    const int oi = blockIdx.y / p.K, k = blockIdx.y % p.K;
+    const FcOffsets o = fc_offsets(seat_in_dim(p.seat[oi]));
+    const float4* src = reinterpret_cast<const float4*>(p.opp[oi] + (int64_t)k * p.opp_pitch[oi] + o.fc2w);
+    float m = 0.f;
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < H2 * H1 / 4; f += gridDim.x * blockDim.x) {
+        const float4 w = src[f];
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(w.x), fabsf(w.y))), fmaxf(fabsf(w.z), fabsf(w.w)));
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0) atomicMax(p.wmax + blockIdx.y, __float_as_uint(m));      // m >= 0: bit order = value order
+}
 
 __global__ void __launch_bounds__(256) ls_split_w2_kernel(const LsPrepParams p) {
     const int oi = blockIdx.y / p.K, k = blockIdx.y % p.K;
     const FcOffsets o = fc_offsets(seat_in_dim(p.seat[oi]));
     const float4* src = reinterpret_cast<const float4*>(p.opp[oi] + (int64_t)k * p.opp_pitch[oi] + o.fc2w);
-    float4* hi = reinterpret_cast<float4*>(p.w2split + (size_t)(blockIdx.y * 2 + 0) * H2 * H1);
-    float4* lo = reinterpret_cast<float4*>(p.w2split + (size_t)(blockIdx.y * 2 + 1) * H2 * H1);
+    const float sw = ldexpf(1.0f, ls_scale_exp(__uint_as_float(p.wmax[blockIdx.y]), 14));
+    uint2* hi = reinterpret_cast<uint2*>(p.w2split + (size_t)(blockIdx.y * 2 + 0) * H2 * H1);
+    uint2* lo = reinterpret_cast<uint2*>(p.w2split + (size_t)(blockIdx.y * 2 + 1) * H2 * H1);
     for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < H2 * H1 / 4; f += gridDim.x * blockDim.x) {
         const float4 w = src[f];
-        float4 h, l;
-        h.x = tf32_rna(w.x); l.x = tf32_rna(w.x - h.x);
-        h.y = tf32_rna(w.y); l.y = tf32_rna(w.y - h.y);
-        h.z = tf32_rna(w.z); l.z = tf32_rna(w.z - h.z);
-        h.w = tf32_rna(w.w); l.w = tf32_rna(w.w - h.w);
-        hi[f] = h;
-        lo[f] = l;
+        const float v[4] = {w.x * sw, w.y * sw, w.z * sw, w.w * sw};
+        __half h[4], l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            h[i] = __float2half_rn(v[i]);
+            l[i] = __float2half_rn(v[i] - __half2float(h[i]));
+        }
+        const __half2 h01 = __halves2half2(h[0], h[1]), h23 = __halves2half2(h[2], h[3]);
+        const __half2 l01 = __halves2half2(l[0], l[1]), l23 = __halves2half2(l[2], l[3]);
+        hi[f] = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+        lo[f] = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
     }
 }
 
@@ -289,8 +327,33 @@ __device__ __forceinline__ void ls_l1stats_row(const float* __restrict__ row, in
 
 __global__ void __launch_bounds__(512) ls_l1stats_kernel(const LsPrepParams p) {
     const int oi = blockIdx.x / p.K, k = blockIdx.x % p.K;
-    ls_l1stats_row(p.opp[oi] + (int64_t)k * p.opp_pitch[oi], seat_in_dim(p.seat[oi]),
-                   p.l1stats + (size_t)blockIdx.x * LS_L1S);
+    const int in = seat_in_dim(p.seat[oi]);
+    const float* row = p.opp[oi] + (int64_t)k * p.opp_pitch[oi];
+    ls_l1stats_row(row, in, p.l1stats + (size_t)blockIdx.x * LS_L1S);
+    // FP16 operand scales of this opponent (see the note above ls_wmax_kernel)
+    __shared__ float red[2][16];
+    const int t = threadIdx.x;
+    float g = fabsf(row[H1 * in + H1 + t]), be = fabsf(row[H1 * in + 2 * H1 + t]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        g = fmaxf(g, __shfl_xor_sync(0xffffffffu, g, off));
+        be = fmaxf(be, __shfl_xor_sync(0xffffffffu, be, off));
+    }
+    if ((t & 31) == 0) {
+        red[0][t >> 5] = g;
+        red[1][t >> 5] = be;
+    }
+    __syncthreads();
+    if (t == 0) {
+        for (int w = 1; w < 16; ++w) {
+            g = fmaxf(g, red[0][w]);
+            be = fmaxf(be, red[1][w]);
+        }
+        const int sx = ls_scale_exp(22.63f * g + be, 13);
+        const int sw = ls_scale_exp(__uint_as_float(p.wmax[blockIdx.x]), 14);
+        p.oscale[blockIdx.x * 2 + 0] = ldexpf(1.0f, sx);
+        p.oscale[blockIdx.x * 2 + 1] = ldexpf(1.0f, -(sx + sw));
+    }
 }
 
 // the same statistics for every member row (tensor-core member form), once per rollout
@@ -317,9 +380,9 @@ constexpr int LS_W1A_FLOATS = H1 * IN_GOOD + 3 * H1;
 // ---------------------------------------------------------------------------------------------
 constexpr int OP_THREADS = 448;                   // warps 0-3 epilogue, 4-11 A producers, 12 TMA, 13 MMA
 constexpr int OP_PROD = 256;
-constexpr int OP_BM = 128, OP_BN = 256, OP_BK = 32, OP_KT = H1 / OP_BK;
-constexpr uint32_t OP_A_BYTES = OP_BM * OP_BK * 4;          // 16 KB
-constexpr uint32_t OP_B_BYTES = OP_BN * OP_BK * 4;          // 32 KB
+constexpr int OP_BM = 128, OP_BN = 256, OP_BK = 64, OP_KT = H1 / OP_BK;   // 64 fp16 = one 128-byte swizzle row
+constexpr uint32_t OP_A_BYTES = OP_BM * OP_BK * 2;          // 16 KB
+constexpr uint32_t OP_B_BYTES = OP_BN * OP_BK * 2;          // 32 KB
 constexpr uint32_t OP_STAGE_BYTES = 2 * OP_A_BYTES + 2 * OP_B_BYTES;   // A hi | A lo | B hi | B lo = 96 KB
 constexpr int OP_STAGES = 2;
 constexpr size_t OP_OFF_W1A = (size_t)OP_STAGES * OP_STAGE_BYTES;
@@ -328,8 +391,8 @@ constexpr size_t OP_OFF_BAR = OP_OFF_TAIL + (size_t)LS_TAIL_FLOATS * 4;
 constexpr size_t OP_SMEM_MAX = 232448;                                     // 227 KB opt-in limit per CTA
 constexpr size_t OP_SLACK = OP_SMEM_MAX - (OP_OFF_BAR + 128);              // what is left for the 1024-byte alignment
 constexpr size_t OP_SMEM = OP_SMEM_MAX;
-constexpr uint32_t OP_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(OP_BN >> 3) << 17) |
-                              ((uint32_t)(OP_BM >> 4) << 24);
+// instruction descriptor: D = F32, A = B = F16 (format 0), both K-major, M = 128, N = 256
+constexpr uint32_t OP_IDESC = (1u << 4) | ((uint32_t)(OP_BN >> 3) << 17) | ((uint32_t)(OP_BM >> 4) << 24);
 
 struct LsOppParams {
     const float* opp[2];
@@ -342,67 +405,70 @@ struct LsOppParams {
     int32_t* act;            // [3][N]
     float* gap;
     const double* l1stats;
+    const float* oscale;     // [2 seats][K][2]: activation scale, accumulator unscale
     int32_t* status;
     float* logits;           // this cycle's [3][N][5] (parity instrumentation; null in production)
 };
 
-__device__ __forceinline__ void op_umma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(OP_IDESC), "r"(accumulate)
-        : "memory");
-}
-
-// One producer thread's share of an A tile: 16-byte chunk c (4 activations) of k-tile kt for its FOUR
-// episode rows lane + 32 j: relu(LN1(W1 x + b1)), split into TF32 hi + lo and stored K-major with the
-// 128-byte swizzle the UMMA descriptor expects (chunk c of row r at c ^ (r & 7)).  The weight loads are
-// warp-uniform (producer warp = chunk) and serve four rows each: a shared-memory broadcast costs four
-// wavefronts per LDS.128, and with one row per thread the LSU pipe bounded the producers.  Rows of a
-// quarter warp differ in (r & 7), so the tile stores are conflict-free.
+// One producer thread's share of an A tile: 16-byte chunk c (8 fp16 activations) of k-tile kt for its FOUR
+// episode rows lane + 32 j: relu(LN1(W1 x + b1)) scaled by 2^s_x, split into FP16 hi + lo and stored K-major with
+// the 128-byte swizzle the UMMA descriptor expects (chunk c of row r at c ^ (r & 7)).  The weight loads are
+// warp-uniform (producer warp = chunk) and serve four rows each.  Rows of a quarter warp differ in (r & 7), so
+// the tile stores are conflict-free.
 template <int IN>
 __device__ __forceinline__ void op_produce_chunk(const float* __restrict__ w1a, const float (&x)[4][IN_GOOD],
-                                                 const float (&mean)[4], const float (&rstd)[4], int kt, int c,
+                                                 const float (&mean)[4], const float (&rstd)[4], float sx, int kt, int c,
                                                  int lane, unsigned char* __restrict__ a_hi,
                                                  unsigned char* __restrict__ a_lo) {
     const float* fc1b = w1a + H1 * IN;
     const float* ln1g = fc1b + H1;
     const float* ln1b = ln1g + H1;
-    const int k0 = kt * OP_BK + c * 4;
-    const float4 bb = *reinterpret_cast<const float4*>(fc1b + k0);
-    const float4 gg = *reinterpret_cast<const float4*>(ln1g + k0);
-    const float4 ee = *reinterpret_cast<const float4*>(ln1b + k0);
-    const float bq[4] = {bb.x, bb.y, bb.z, bb.w}, gq[4] = {gg.x, gg.y, gg.z, gg.w}, eq[4] = {ee.x, ee.y, ee.z, ee.w};
-    float hi[4][4], lo[4][4];      // [row j][k]
+    const int k0 = kt * OP_BK + c * 8;
+    uint32_t hi[4][4], lo[4][4];      // [row j][k pair]
 #pragma unroll
-    for (int qq = 0; qq < 4; ++qq) {
-        float w[IN];
-        const float2* wr = reinterpret_cast<const float2*>(w1a + (k0 + qq) * IN);
+    for (int half = 0; half < 2; ++half) {
+        const float4 bb = *reinterpret_cast<const float4*>(fc1b + k0 + 4 * half);
+        const float4 gg = *reinterpret_cast<const float4*>(ln1g + k0 + 4 * half);
+        const float4 ee = *reinterpret_cast<const float4*>(ln1b + k0 + 4 * half);
+        const float bq[4] = {bb.x, bb.y, bb.z, bb.w}, gq[4] = {gg.x, gg.y, gg.z, gg.w}, eq[4] = {ee.x, ee.y, ee.z, ee.w};
+        float hv[4][4];               // [row j][k]
 #pragma unroll
-        for (int i2 = 0; i2 < IN / 2; ++i2) {
-            const float2 v = wr[i2];
-            w[2 * i2] = v.x;
-            w[2 * i2 + 1] = v.y;
+        for (int qq = 0; qq < 4; ++qq) {
+            float w[IN];
+            const float2* wr = reinterpret_cast<const float2*>(w1a + (k0 + 4 * half + qq) * IN);
+#pragma unroll
+            for (int i2 = 0; i2 < IN / 2; ++i2) {
+                const float2 v = wr[i2];
+                w[2 * i2] = v.x;
+                w[2 * i2 + 1] = v.y;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float pre = 0.f;
+#pragma unroll
+                for (int i = 0; i < IN; ++i) pre = fmaf(w[i], x[j][i], pre);
+                pre += bq[qq];
+                hv[j][qq] = fmaxf(fmaf((pre - mean[j]) * rstd[j], gq[qq], eq[qq]), 0.f) * sx;
+            }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float pre = 0.f;
+        for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int i = 0; i < IN; ++i) pre = fmaf(w[i], x[j][i], pre);
-            pre += bq[qq];
-            const float h = fmaxf(fmaf((pre - mean[j]) * rstd[j], gq[qq], eq[qq]), 0.f);
-            // hi = h truncated to TF32 (exactly what the tensor core reads of an fp32 word); lo = h - hi is
-            // exact in fp32 and is itself read truncated: relative error 2^-21, like the dropped lo.lo term
-            hi[j][qq] = __uint_as_float(__float_as_uint(h) & 0xffffe000u);
-            lo[j][qq] = h - hi[j][qq];
-        }
+            for (int pr = 0; pr < 2; ++pr) {
+                // hi = fp16(h'), lo = fp16(h' - hi): the residual is exact in fp32
+                const __half2 h2 = __floats2half2_rn(hv[j][2 * pr], hv[j][2 * pr + 1]);
+                const float2 hf = __half22float2(h2);
+                const __half2 l2 = __floats2half2_rn(hv[j][2 * pr] - hf.x, hv[j][2 * pr + 1] - hf.y);
+                hi[j][2 * half + pr] = *reinterpret_cast<const uint32_t*>(&h2);
+                lo[j][2 * half + pr] = *reinterpret_cast<const uint32_t*>(&l2);
+            }
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int r = lane + 32 * j;
         const int off = r * 128 + ((c ^ (r & 7)) << 4);
-        *reinterpret_cast<float4*>(a_hi + off) = make_float4(hi[j][0], hi[j][1], hi[j][2], hi[j][3]);
-        *reinterpret_cast<float4*>(a_lo + off) = make_float4(lo[j][0], lo[j][1], lo[j][2], lo[j][3]);
+        *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[j][0], hi[j][1], hi[j][2], hi[j][3]);
+        *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[j][0], lo[j][1], lo[j][2], lo[j][3]);
     }
 }
 
@@ -485,6 +551,7 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
                 asm volatile("bar.sync 2, 128;\n" ::: "memory");
                 cur_ok = okey;
             }
+            const float unscale = __ldg(p.oscale + okey * 2 + 1);
             const int64_t j = (int64_t)tile * Geo::ROWS_PER_JOB + q * 32 + lane;
             const bool valid = j < p.PE;
             const int64_t jj = valid ? j : p.PE - 1;
@@ -501,10 +568,10 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
                     const float4 bb = *reinterpret_cast<const float4*>(b2 + c0 + i);
-                    sum += __uint_as_float(v[i]) + bb.x;
-                    sum += __uint_as_float(v[i + 1]) + bb.y;
-                    sum += __uint_as_float(v[i + 2]) + bb.z;
-                    sum += __uint_as_float(v[i + 3]) + bb.w;
+                    sum += fmaf(__uint_as_float(v[i]), unscale, bb.x);          // 2^-(s_w + s_x): exact
+                    sum += fmaf(__uint_as_float(v[i + 1]), unscale, bb.y);
+                    sum += fmaf(__uint_as_float(v[i + 2]), unscale, bb.z);
+                    sum += fmaf(__uint_as_float(v[i + 3]), unscale, bb.w);
                 }
             }
             const float mean = sum * (1.0f / H2);
@@ -519,7 +586,7 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
                     const float bq[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const float d = (__uint_as_float(v[i + u]) + bq[u]) - mean;
+                        const float d = fmaf(__uint_as_float(v[i + u]), unscale, bq[u]) - mean;
                         sq = fmaf(d, d, sq);
                     }
                 }
@@ -542,7 +609,7 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
                     float h[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const float x = (__uint_as_float(v[i + u]) + bq[u]) - mean;
+                        const float x = fmaf(__uint_as_float(v[i + u]), unscale, bq[u]) - mean;
                         h[u] = fmaxf(fmaf(x * rstd, gq[u], eq[u]), 0.f);
                     }
 #pragma unroll
@@ -579,7 +646,7 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
     } else if (warp < 12) {
         // ===================== A producers: layer 1 + LayerNorm + ReLU -> TF32 hi/lo tiles =====
         const int pt = threadIdx.x - 128;
-        const int c = pt >> 5;                        // producer warp = 16-byte chunk (4 k) of every k-tile
+        const int c = pt >> 5;                        // producer warp = 16-byte chunk (8 fp16 k) of every k-tile
         int cur_ok = -1;
         uint32_t it = 0;
         for (int job = job0; job < p.n_jobs; job += job_stride) {
@@ -596,6 +663,7 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
                 asm volatile("bar.sync 1, 256;\n" ::: "memory");
                 cur_ok = okey;
             }
+            const float sx = __ldg(p.oscale + okey * 2);               // 2^s_x of this opponent
             // observations of this thread's four episode rows lane + 32 j
             float x[4][IN_GOOD];
 #pragma unroll
@@ -657,9 +725,9 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
                 unsigned char* a_lo = a_hi + OP_A_BYTES;
 #if !(defined(CEV_EXP) && (CEV_EXP & 1))      // development experiment: bit 0 = producers write nothing
                 if (in == IN_GOOD) {
-                    op_produce_chunk<IN_GOOD>(w1a, x, mean, rstd, kt, c, lane, a_hi, a_lo);
+                    op_produce_chunk<IN_GOOD>(w1a, x, mean, rstd, sx, kt, c, lane, a_hi, a_lo);
                 } else {
-                    op_produce_chunk<IN_ADV>(w1a, x, mean, rstd, kt, c, lane, a_hi, a_lo);
+                    op_produce_chunk<IN_ADV>(w1a, x, mean, rstd, sx, kt, c, lane, a_hi, a_lo);
                 }
 #endif
                 asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic writes -> tensor core reads
@@ -702,9 +770,9 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
                 tc_mbar_wait(bar_full + st, use & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 {
-                    // issued by one elected lane of the converged warp (tc_issue_ktile_3xtf32, tc_common.cuh)
+                    // issued by one elected lane of the converged warp (tc_issue_ktile_3xf16, tc_common.cuh)
                     const uint32_t s_addr = stage_base + st * Geo::STAGE_BYTES;
-                    tc_issue_ktile_3xtf32(d_tmem, umma_desc_sw128(s_addr), umma_desc_sw128(s_addr + OP_A_BYTES),
+                    tc_issue_ktile_3xf16(d_tmem, umma_desc_sw128(s_addr), umma_desc_sw128(s_addr + OP_A_BYTES),
                                           umma_desc_sw128(s_addr + 2 * OP_A_BYTES),
                                           umma_desc_sw128(s_addr + 2 * OP_A_BYTES + Geo::B_BYTES), OP_IDESC, kt ? 1u : 0u,
                                           tc_smem_u32(bar_empty + st));
@@ -730,8 +798,8 @@ namespace cev {
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-// opponent preparation (2) + member layer-1 statistics + initial states + 3 kernels per world step
-int rollout_lockstep_launches(int n_cycles) { return 4 + 3 * n_cycles; }
+// opponent preparation (3) + member layer-1 statistics + initial states + 3 kernels per world step
+int rollout_lockstep_launches(int n_cycles) { return 5 + 3 * n_cycles; }
 
 // How the SMs are shared out between the two persistent kernels of a world step (tensor-core member form).
 // The opponent kernel is bound by the tensor pipe of the SMs it gets (~20 us per 128-episode job, ~15 us to get
@@ -815,7 +883,11 @@ static int ls_build_role(cev_handle* h, const ClusterParams& p, void* ws, cudaSt
     }
     pp.K = p.K;
     pp.w2split = b.w2split;
+    pp.wmax = b.wmax;
+    pp.oscale = b.oscale;
     pp.l1stats = b.l1stats;
+    CEV_CUDA(cudaMemsetAsync(b.wmax, 0, (size_t)2 * p.K * sizeof(uint32_t), stream));
+    ls_wmax_kernel<<<dim3(32, 2 * p.K), 256, 0, stream>>>(pp);
     ls_split_w2_kernel<<<dim3(32, 2 * p.K), 256, 0, stream>>>(pp);
     ls_l1stats_kernel<<<2 * p.K, 512, 0, stream>>>(pp);
     ls_member_l1stats_kernel<<<p.P, 512, 0, stream>>>(p.members, p.member_pitch, seat_in_dim(ms), b.ml1stats);
@@ -837,10 +909,10 @@ static int ls_build_role(cev_handle* h, const ClusterParams& p, void* ws, cudaSt
     }
     {
         cuuint64_t dims[2] = {(cuuint64_t)H1, (cuuint64_t)2 * p.K * 2 * H2};
-        cuuint64_t strides[1] = {(cuuint64_t)H1 * 4};
+        cuuint64_t strides[1] = {(cuuint64_t)H1 * sizeof(__half)};
         cuuint32_t box[2] = {OP_BK, OP_BN};
         cuuint32_t estr[2] = {1, 1};
-        CUresult r = encode(&c->map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, b.w2split, dims, strides, box, estr,
+        CUresult r = encode(&c->map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, b.w2split, dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
@@ -884,6 +956,7 @@ static int ls_build_role(cev_handle* h, const ClusterParams& p, void* ws, cudaSt
     op.act = b.act;
     op.gap = b.gap;
     op.l1stats = b.l1stats;
+    op.oscale = b.oscale;
     op.status = p.status;
 
     LsMemberTcParams& tp = c->tp;

@@ -158,6 +158,37 @@ __device__ __forceinline__ void tc_issue_ktile_3xtf32(uint32_t d_tmem, uint64_t 
         "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(accumulate), "r"(bar_empty), "r"(idesc)
         : "memory");
 }
+// the same twelve MMAs with kind::f16 operands (K = 16 per instruction: a 128-byte swizzle row holds 64 k)
+__device__ __forceinline__ void tc_issue_ktile_3xf16(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                                      uint32_t idesc, uint32_t accumulate, uint32_t bar_empty) {
+    asm volatile(
+        "{\n"
+        ".reg .pred pe, pa, pt;\n"
+        ".reg .b64 ah1, ah2, ah3, al1, al2, al3, bh1, bh2, bh3, bl1, bl2, bl3;\n"
+        "elect.sync _|pe, 0xffffffff;\n"
+        "setp.ne.b32 pa, %5, 0;\n"
+        "setp.eq.b32 pt, 0, 0;\n"
+        "add.s64 ah1, %1, 2;\n add.s64 ah2, %1, 4;\n add.s64 ah3, %1, 6;\n"
+        "add.s64 al1, %2, 2;\n add.s64 al2, %2, 4;\n add.s64 al3, %2, 6;\n"
+        "add.s64 bh1, %3, 2;\n add.s64 bh2, %3, 4;\n add.s64 bh3, %3, 6;\n"
+        "add.s64 bl1, %4, 2;\n add.s64 bl2, %4, 4;\n add.s64 bl3, %4, 6;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %2, %3, %7, pa;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %4, %7, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %3, %7, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], al1, bh1, %7, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], ah1, bl1, %7, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], ah1, bh1, %7, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], al2, bh2, %7, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], ah2, bl2, %7, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], ah2, bh2, %7, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], al3, bh3, %7, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], ah3, bl3, %7, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], ah3, bh3, %7, pt;\n"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(accumulate), "r"(bar_empty), "r"(idesc)
+        : "memory");
+}
 __device__ __forceinline__ void tc_commit_elected(uint32_t bar) {
     asm volatile(
         "{\n.reg .pred pe;\nelect.sync _|pe, 0xffffffff;\n"

@@ -126,8 +126,8 @@ def test_lockstep_kernels_match_oracle_on_multi_tile_shapes(member_role, P, K, E
 
 def test_lockstep_is_the_auto_choice_for_es_shapes_and_counts_its_launches():
     from coevonet_b200 import ops
-    # opponent split + layer-1 statistics, member layer-1 statistics, initial states, 3 kernels per world step
-    assert ops.rollout_plan(0, 1024, 1, 16) == (3, 4 + 3 * 25)
+    # opponent max + split + layer-1 statistics, member layer-1 statistics, initial states, 3 kernels per world step
+    assert ops.rollout_plan(0, 1024, 1, 16) == (3, 5 + 3 * 25)
     assert ops.rollout_plan(0, 20, 3, 1)[0] == 2
     assert ops.rollout_plan(0, 8192, 1, 1)[0] == 3          # GA shape at scale: lockstep too
     assert ops.rollout_plan(0, 1, 1, 10)[0] == 2
