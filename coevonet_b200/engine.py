@@ -175,7 +175,8 @@ class _EngineBase:
             [args.mutation_power_agent_0, args.mutation_power_agent_1, args.mutation_power_adversary],
             self.hist_cap, self.device)
         self._eval_init_tag = 0x40000000
-        self._pending_status = None       # (pinned host copy, event) of the previous generation
+        #: (pinned host copy, event) of the generations whose status word has not been looked at yet, oldest first
+        self._pending_status = []
 
     # -- replicated / sharded state helpers -----------------------------------------------------
     def sigma_dev(self, role):
@@ -212,26 +213,29 @@ class _EngineBase:
     # -- status word: examined one generation late, without a sync ---------------------------------
     def _post_status(self):
         if self.device.type != "cuda":
-            self._pending_status = (self.status.clone(), None)
+            self._pending_status.append((self.status.clone(), None))
             return
         host = torch.empty(1, dtype=torch.int32).pin_memory()
         host.copy_(self.status, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
-        self._pending_status = (host, ev)
+        self._pending_status.append((host, ev))
 
-    def _raise_pending_status(self):
-        if self._pending_status is None:
-            return
-        host, ev = self._pending_status
-        self._pending_status = None
-        if ev is not None:
-            ev.synchronize()          # recorded a whole generation ago: already complete in steady state
-        self.k.raise_on_status(host)
+    def _raise_pending_status(self, keep=1):
+        """Look at the status words posted so far, except the newest ``keep``.  A generation starts by checking
+        the generation BEFORE the previous one: the previous one's copy was enqueued a moment ago, and waiting
+        for it would stop the host from running ahead of the device (0.5 ms of idle device per generation)."""
+        if self.device.type != "cuda":
+            keep = 0
+        while len(self._pending_status) > keep:
+            host, ev = self._pending_status.pop(0)
+            if ev is not None:
+                ev.synchronize()      # recorded at least a whole generation ago: complete in steady state
+            self.k.raise_on_status(host)
 
     def check_status(self):
         """Surface device-detected faults now (synchronises): the reference's ``ValueError``."""
-        self._raise_pending_status()
+        self._raise_pending_status(keep=0)
         self.k.raise_on_status(self.status)
 
     def _role_slot(self, out, role, limit):
@@ -387,7 +391,7 @@ class _EngineBase:
         self.gstate.copy_(gs.to(self.device))
         if sd.get("env") is not None and hasattr(self.env, "load_state_dict"):
             self.env.load_state_dict(sd["env"])
-        self._pending_status = None
+        self._pending_status = []
 
 
 # ---------------------------------------------------------------------------
