@@ -20,10 +20,11 @@
 //                     first-max argmax in the epilogue warps.  Runs on a share of the SMs BESIDE ls_opp_kernel.
 //   ls_opp_kernel     persistent, one CTA per SM, job = (opponent seat, opponent set, 128 episodes):
 //                     8 producer warps (warp = 16-byte k chunk, lane = 4 episode rows) compute layer 1 +
-//                     LayerNorm + ReLU and write the activations, split into TF32 hi + lo parts,
-//                     straight into the 128B-swizzled K-major A tiles; one thread streams the pre-split opponent fc2
-//                     matrix with TMA; one thread issues tcgen05.mma kind::tf32 (M=128, N=256, K=8)
-//                     three times per k-step (hi.hi + lo.hi + hi.lo = "3xTF32", fp32-level accuracy)
+//                     LayerNorm + ReLU and write the activations, scaled by a power of two and split into FP16
+//                     hi + lo parts, straight into the 128B-swizzled K-major A tiles; one thread streams the
+//                     pre-split (scaled FP16 hi + lo) opponent fc2 matrix with TMA; one warp issues
+//                     tcgen05.mma kind::f16 (M=128, N=256, K=16) three times per k-step (lo.hi + hi.lo + hi.hi:
+//                     22-23 significand bits per operand, fp32-level accuracy, at twice the TF32 rate)
 //                     into a double-buffered TMEM accumulator; 4 epilogue warps read it back with
 //                     tcgen05.ld and do bias + LayerNorm-2 + ReLU + output layer + argmax per row.
 //                     Layer-1 LayerNorm statistics come from the closed form mean = wbar.x + bbar,
@@ -32,8 +33,9 @@
 //   ls_env_step_kernel one thread per episode: fp64 physics, rewards, next observations
 //                     (bit-exact with oracle/mpe_env.py given equal actions).
 //
-// Arithmetic: member and opponent fc2 3xTF32 with fp32 accumulation, layer 1 / LayerNorm / output fp32 (error
-// ~1e-6 of the activations' scale, the same order as fp32 summation-order noise); environment fp64.
+// Arithmetic: member fc2 3xTF32, opponent fc2 the scaled two-term FP16 split, both with fp32 accumulation; layer 1 /
+// LayerNorm / output fp32 (error ~1e-6 of the activations' scale, the same order as fp32 summation-order noise);
+// environment fp64.
 #include <stdlib.h>
 
 #include <cuda_fp16.h>
@@ -376,7 +378,7 @@ constexpr int LS_TAIL_FLOATS = 2056;              // fc2.b | ln2.g | ln2.b | out
 constexpr int LS_W1A_FLOATS = H1 * IN_GOOD + 3 * H1;
 
 // ---------------------------------------------------------------------------------------------
-// opponent forward (tcgen05, 3xTF32)
+// opponent forward (tcgen05, scaled two-term FP16 split)
 // ---------------------------------------------------------------------------------------------
 constexpr int OP_THREADS = 448;                   // warps 0-3 epilogue, 4-11 A producers, 12 TMA, 13 MMA
 constexpr int OP_PROD = 256;
@@ -644,7 +646,7 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
             }
         }
     } else if (warp < 12) {
-        // ===================== A producers: layer 1 + LayerNorm + ReLU -> TF32 hi/lo tiles =====
+        // ===================== A producers: layer 1 + LayerNorm + ReLU -> FP16 hi/lo tiles =====
         const int pt = threadIdx.x - 128;
         const int c = pt >> 5;                        // producer warp = 16-byte chunk (8 fp16 k) of every k-tile
         int cur_ok = -1;
@@ -859,9 +861,10 @@ static int ls_reserve(cev_handle* h, size_t need) {
     return CEV_OK;
 }
 
-// Launches the once-per-rollout preparation of one role on `stream` (TF32 split of the opponents' fc2, layer-1
-// statistics of the opponents and, for the tensor-core member form, of every member row) and fills the context.
-static int ls_build_role(cev_handle* h, const ClusterParams& p, void* ws, cudaStream_t stream, LsRoleCtx* c) {
+// Launches the once-per-rollout preparation of one role (on `stream`: FP16 split of the opponents' fc2 and their
+// layer-1 statistics; on `stream_m`: the layer-1 statistics of every member row) and fills the context.
+static int ls_build_role(cev_handle* h, const ClusterParams& p, void* ws, cudaStream_t stream, cudaStream_t stream_m,
+                         LsRoleCtx* c) {
     EncodeTiledFn encode = get_encode_fn();
     if (!encode) {
         set_error("rollout_lockstep: cuTensorMapEncodeTiled is not available from the driver");
@@ -874,7 +877,7 @@ static int ls_build_role(cev_handle* h, const ClusterParams& p, void* ws, cudaSt
     c->ms = ms;
     const int seat_of[2] = {ms == 0 ? 1 : 0, ms == 2 ? 1 : 2};
 
-    // ---- opponents: TF32 split + layer-1 statistics ------------------------------------------
+    // ---- opponents: scaled FP16 split + layer-1 statistics -----------------------------------
     LsPrepParams pp{};
     for (int oi = 0; oi < 2; ++oi) {
         pp.opp[oi] = p.opp[oi];
@@ -890,7 +893,7 @@ static int ls_build_role(cev_handle* h, const ClusterParams& p, void* ws, cudaSt
     ls_wmax_kernel<<<dim3(32, 2 * p.K), 256, 0, stream>>>(pp);
     ls_split_w2_kernel<<<dim3(32, 2 * p.K), 256, 0, stream>>>(pp);
     ls_l1stats_kernel<<<2 * p.K, 512, 0, stream>>>(pp);
-    ls_member_l1stats_kernel<<<p.P, 512, 0, stream>>>(p.members, p.member_pitch, seat_in_dim(ms), b.ml1stats);
+    ls_member_l1stats_kernel<<<p.P, 512, 0, stream_m>>>(p.members, p.member_pitch, seat_in_dim(ms), b.ml1stats);
 
     // ---- tensor maps ---------------------------------------------------------------------------
     const FcOffsets om = fc_offsets(seat_in_dim(ms));
@@ -989,7 +992,7 @@ int launch_rollout_lockstep(cev_handle* h, const ClusterParams& p, cudaStream_t 
     rc = ls_configure(h);
     if (rc) return rc;
     LsRoleCtx ctx;
-    rc = ls_build_role(h, p, h->ls_workspace, stream, &ctx);
+    rc = ls_build_role(h, p, h->ls_workspace, stream, stream, &ctx);
     if (rc) return rc;
     LsEnvParams& ep = ctx.ep;
     LsOppParams& op = ctx.op;
@@ -1113,12 +1116,29 @@ int launch_rollout_lockstep_roles(cev_handle* h, const ClusterParams* ps, int n_
             CEV_CUDA(cudaEventCreateWithFlags(&h->ev_env[r], cudaEventDisableTiming));
         }
     }
+    // Consecutive kernels of one kind alternate between two streams, so the next role's CTAs move in as the previous
+    // role's CTAs retire (no idle tail at the end of every kernel, launch latency hidden).
+    static const int alt = getenv("CEV_LS_ALT") ? atoi(getenv("CEV_LS_ALT")) : 1;
+    static const int skip = getenv("CEV_LS_SKIP") ? atoi(getenv("CEV_LS_SKIP")) : 0;   // development aid, see the single-role path
+    cudaStream_t s_mem[2] = {stream, alt ? h->mem_stream2 : stream};
+    cudaStream_t s_opp[2] = {h->opp_stream2[0], alt ? h->opp_stream2[1] : h->opp_stream2[0]};
+    cudaStream_t s_env = h->env_stream;
+    CEV_CUDA(cudaEventRecord(h->fork_ev, stream));                  // everything before this call is on `stream`
+    CEV_CUDA(cudaStreamWaitEvent(s_opp[0], h->fork_ev, 0));
+    CEV_CUDA(cudaStreamWaitEvent(s_opp[1], h->fork_ev, 0));
+    CEV_CUDA(cudaStreamWaitEvent(s_mem[1], h->fork_ev, 0));
+    CEV_CUDA(cudaStreamWaitEvent(s_env, h->fork_ev, 0));
+    // Every role's preparation goes on the streams of its first kernels: the opponents' split / statistics in front
+    // of its first opponent kernel, the members' statistics and the initial states in front of its first member
+    // kernel (ev_env[r] tells the opponent stream that the initial observations exist), so the roles prepare side by
+    // side and behind one another's first kernels instead of one after the other in front of the whole pass.
     LsRoleCtx ctx[CEV_MAX_ROLES];
     for (int r = 0; r < n_roles; ++r) {
-        rc = ls_build_role(h, ps[r], static_cast<char*>(h->ls_workspace) + per_role * r, stream, &ctx[r]);
+        rc = ls_build_role(h, ps[r], static_cast<char*>(h->ls_workspace) + per_role * r, s_opp[r & 1], s_mem[r & 1], &ctx[r]);
         if (rc) return rc;
         ctx[r].ep.last = ps[r].n_cycles == 0;
-        ls_init_kernel<<<ctx[r].env_blocks, 256, 0, stream>>>(ctx[r].ep);
+        ls_init_kernel<<<ctx[r].env_blocks, 256, 0, s_mem[r & 1]>>>(ctx[r].ep);
+        CEV_CUDA(cudaEventRecord(h->ev_env[r], s_mem[r & 1]));
     }
     int opp_grid = 0, mem_grid = 0;
     ls_split_sms(h->n_sm, ctx[0].op.n_jobs, ctx[0].tp.n_jobs, &opp_grid, &mem_grid);
@@ -1129,27 +1149,14 @@ int launch_rollout_lockstep_roles(cev_handle* h, const ClusterParams* ps, int n_
     if (ctx[0].op.n_jobs < opp_grid) opp_grid = ctx[0].op.n_jobs;
     if (ctx[0].tp.n_jobs < mem_grid) mem_grid = ctx[0].tp.n_jobs;
 
-    // Consecutive kernels of one kind alternate between two streams, so the next role's CTAs move in as the previous
-    // role's CTAs retire (no idle tail at the end of every kernel, launch latency hidden).
-    static const int alt = getenv("CEV_LS_ALT") ? atoi(getenv("CEV_LS_ALT")) : 1;
-    static const int skip = getenv("CEV_LS_SKIP") ? atoi(getenv("CEV_LS_SKIP")) : 0;   // development aid, see the single-role path
-    cudaStream_t s_mem[2] = {stream, alt ? h->mem_stream2 : stream};
-    cudaStream_t s_opp[2] = {h->opp_stream2[0], alt ? h->opp_stream2[1] : h->opp_stream2[0]};
-    cudaStream_t s_env = h->env_stream;
-    CEV_CUDA(cudaEventRecord(h->fork_ev, stream));                  // preparation + initial states are on `stream`
-    CEV_CUDA(cudaStreamWaitEvent(s_opp[0], h->fork_ev, 0));
-    CEV_CUDA(cudaStreamWaitEvent(s_opp[1], h->fork_ev, 0));
-    CEV_CUDA(cudaStreamWaitEvent(s_mem[1], h->fork_ev, 0));
-    CEV_CUDA(cudaStreamWaitEvent(s_env, h->fork_ev, 0));
     const int n_cycles = p0.n_cycles;
     int i = 0;
     for (int c = 0; c < n_cycles; ++c) {
         for (int r = 0; r < n_roles; ++r, ++i) {
             cudaStream_t so = s_opp[i & 1], sm = s_mem[i & 1];
-            if (c > 0) {                                            // this role's previous environment step
-                CEV_CUDA(cudaStreamWaitEvent(so, h->ev_env[r], 0));
-                CEV_CUDA(cudaStreamWaitEvent(sm, h->ev_env[r], 0));
-            }
+            // this role's previous environment step (c = 0: its initial states, issued on the member stream)
+            CEV_CUDA(cudaStreamWaitEvent(so, h->ev_env[r], 0));
+            if (c > 0) CEV_CUDA(cudaStreamWaitEvent(sm, h->ev_env[r], 0));
             if (!(skip & 1)) ls_opp_kernel<<<opp_grid, OP_THREADS, OP_SMEM, so>>>(ctx[r].map_b, ctx[r].op);
             CEV_CUDA(cudaEventRecord(h->ev_opp[r], so));
             if (!(skip & 2)) ls_launch_member_tc(ctx[r], mem_grid, sm);
@@ -1161,9 +1168,16 @@ int launch_rollout_lockstep_roles(cev_handle* h, const ClusterParams* ps, int n_
             CEV_CUDA(cudaEventRecord(h->ev_env[r], s_env));
         }
     }
-    // join: the environment steps wait for every member / opponent kernel of their role, and s_env is in order
+    // join: the environment steps wait for every member / opponent kernel of their role, and s_env is in order; the
+    // other streams are joined too (with no world step to play they hold the preparation and the initial states)
     CEV_CUDA(cudaEventRecord(h->join_ev, s_env));
     CEV_CUDA(cudaStreamWaitEvent(stream, h->join_ev, 0));
+    cudaStream_t others[3] = {s_opp[0], s_opp[1], s_mem[1]};
+    for (int k = 0; k < 3; ++k) {
+        if (others[k] == stream) continue;
+        CEV_CUDA(cudaEventRecord(h->ev_opp[k], others[k]));
+        CEV_CUDA(cudaStreamWaitEvent(stream, h->ev_opp[k], 0));
+    }
     return check_cuda(cudaGetLastError(), "rollout_lockstep (roles) launch");
 }
 

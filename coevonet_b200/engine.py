@@ -70,8 +70,13 @@ class Comm:
     def all_gather_rows(self, local, shard):
         """local [n_local, ...] -> [P, ...] in global row order: ONE collective into one tensor
         (uneven shards are padded to the largest block)."""
+        return self.all_gather_rows_start(local, shard)()
+
+    def all_gather_rows_start(self, local, shard):
+        """Start that collective and return ``finish() -> gathered tensor``: work issued between the two calls
+        (on the current stream) overlaps the collective and, more to the point, the wait for the slowest rank."""
         if not self.enabled:
-            return local
+            return lambda: local
         nmax = max(shard.counts)
         tail = tuple(local.shape[1:])
         if local.shape[0] == nmax:
@@ -80,11 +85,16 @@ class Comm:
             pad = torch.zeros((nmax,) + tail, dtype=local.dtype, device=local.device)
             pad[:local.shape[0]] = local
         out = torch.empty((self.world * nmax,) + tail, dtype=local.dtype, device=local.device)
-        dist.all_gather_into_tensor(out, pad, group=self.group)
-        if shard.P == self.world * nmax:
-            return out
-        out = out.view((self.world, nmax) + tail)
-        return torch.cat([out[r, :shard.counts[r]] for r in range(self.world)], dim=0)
+        work = dist.all_gather_into_tensor(out, pad, group=self.group, async_op=True)
+
+        def finish(out=out, pad=pad):
+            work.wait()               # NCCL: the current stream waits, the host does not
+            if shard.P == self.world * nmax:
+                return out
+            o = out.view((self.world, nmax) + tail)
+            return torch.cat([o[r, :shard.counts[r]] for r in range(self.world)], dim=0)
+
+        return finish
 
     def all_reduce_sum(self, t):
         if self.enabled:
@@ -676,15 +686,21 @@ class ESEngine(_EngineBase):
             cols += [self.k.diversity_dist(self.members[r], self.theta[r], layout.OBS_DIM[r]).to(torch.float64)
                      for r in ROLES]
         packed = torch.stack(cols, dim=1).contiguous()                             # [n_local, 3 or 6]
-        allp = self.comm.all_gather_rows(packed, self.shard)                       # [P, 3 or 6]
-        for i, role in enumerate(ROLES):
-            if a.fitness_sharing:
-                div = self.k.diversity_from_dist(allp[:, 3 + i].to(torch.float32))
-                self.diversity[role] = div
-                fit_local[role] = (fit_local[role].to(torch.float32) / (1 + div)).to(torch.float64)
-                self.fitness[role] = (allp[:, i].to(torch.float32) / (1 + div)).to(torch.float64)
-            else:
-                self.fitness[role] = allp[:, i].contiguous()
+        gathered = self.comm.all_gather_rows_start(packed, self.shard)             # -> [P, 3 or 6]
+
+        def finish_fitness():
+            allp = gathered()
+            for i, role in enumerate(ROLES):
+                if a.fitness_sharing:
+                    div = self.k.diversity_from_dist(allp[:, 3 + i].to(torch.float32))
+                    self.diversity[role] = div
+                    fit_local[role] = (fit_local[role].to(torch.float32) / (1 + div)).to(torch.float64)
+                    self.fitness[role] = (allp[:, i].to(torch.float32) / (1 + div)).to(torch.float64)
+                else:
+                    self.fitness[role] = allp[:, i].contiguous()
+
+        if a.fitness_sharing:
+            finish_fitness()              # the update needs the shared fitness
         for role in ROLES:
             in_dim = layout.OBS_DIM[role]
             if self.update_from_members and hasattr(self.k, "es_update_members"):
@@ -695,6 +711,8 @@ class ESEngine(_EngineBase):
             else:
                 self.k.es_update(fit_local[role].contiguous(), in_dim, self.sigma_dev(role), a.learning_rate,
                                  self.P, self.seed, role, self.gen, self.shard.row0, out=self.last_delta[role])
+        if not a.fitness_sharing:
+            finish_fitness()              # the global fitness is a record only: gathered under the three K6 launches
         self.comm.all_reduce_sum(self.delta_cat)
         self._join_eval()                 # the previous generation's evaluation games read theta
         self.k.axpy(1.0, self.delta_cat, self.theta_cat)
