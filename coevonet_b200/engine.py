@@ -16,7 +16,8 @@ A generation is issued without a host round trip: the mutation
 powers, the evaluation-reward history, the early-stopping counters and the
 generation counter live in a device array (``cev_generation_end_f64``), kernels
 read sigma from it, elite indices stay on the device, and the non-finite status
-word is copied back asynchronously and examined one generation later.
+word is copied back asynchronously and examined two generations later (so the host
+runs one generation ahead of the device).
 ``step()`` reads the evaluation triple back (one sync) only when asked to.
 
 Everything numeric goes through ``self.k`` -- by default ``coevonet_b200.ops``
@@ -220,7 +221,7 @@ class _EngineBase:
         out = self.k.init_states(self.seed, stream_tag, shard.n_local * K * E, self.device, rec0=rec0)
         return out.reshape(shard.n_local, K, E, mpe_spec.INIT_STATE_DIM)
 
-    # -- status word: examined one generation late, without a sync ---------------------------------
+    # -- status word: examined two generations late, without a sync --------------------------------
     def _post_status(self):
         if self.device.type != "cuda":
             self._pending_status.append((self.status.clone(), None))
@@ -686,7 +687,12 @@ class ESEngine(_EngineBase):
             cols += [self.k.diversity_dist(self.members[r], self.theta[r], layout.OBS_DIM[r]).to(torch.float64)
                      for r in ROLES]
         packed = torch.stack(cols, dim=1).contiguous()                             # [n_local, 3 or 6]
-        gathered = self.comm.all_gather_rows_start(packed, self.shard)             # -> [P, 3 or 6]
+        start = getattr(self.comm, "all_gather_rows_start", None)                  # injected comms may only gather
+        if start is not None:
+            gathered = start(packed, self.shard)                                   # -> [P, 3 or 6]
+        else:
+            _all = self.comm.all_gather_rows(packed, self.shard)
+            gathered = lambda: _all
 
         def finish_fitness():
             allp = gathered()
