@@ -804,8 +804,7 @@ namespace cev {
 int rollout_lockstep_launches(int n_cycles) { return 5 + 3 * n_cycles; }
 
 // How the SMs are shared out between the two persistent kernels of a world step (tensor-core member form).
-// The opponent kernel is bound by the tensor pipe of the SMs it gets (~20 us per 128-episode job, ~15 us to get
-// going); a member job streams 512 KB and takes ~8.6 us on its SM until the HBM rate (~6 TB/s over all member CTAs)
+// The opponent kernel is bound by the SMs it gets (~14 us per 128-episode job, ~12 us to get going); a member job streams 512 KB and takes ~8.6 us on its SM until the HBM rate (~6 TB/s over all member CTAs)
 // becomes the limit.  Both end when their slowest CTA ends, so the split that minimises the later of the two is
 // found by trying every one (148 candidates, host side).
 static void ls_split_sms(int n_sm, int opp_jobs, int mem_jobs, int* g_opp, int* g_mem) {
@@ -815,7 +814,7 @@ static void ls_split_sms(int n_sm, int opp_jobs, int mem_jobs, int* g_opp, int* 
         const int gm = n_sm - g;
         const int mg = mem_jobs < gm ? mem_jobs : gm, og = opp_jobs < g ? opp_jobs : g;
         const double t_job_mem = fmax(8.6, mg * 0.0873);
-        const double t_opp = 15.0 + 20.0 * ((opp_jobs + og - 1) / og);
+        const double t_opp = 12.0 + 14.0 * ((opp_jobs + og - 1) / og);
         const double t_mem = 4.0 + t_job_mem * ((mem_jobs + mg - 1) / mg);
         const double t = fmax(t_opp, t_mem);
         if (t < best - 1e-9) {
