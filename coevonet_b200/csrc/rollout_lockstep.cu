@@ -804,8 +804,8 @@ namespace cev {
 int rollout_lockstep_launches(int n_cycles) { return 5 + 3 * n_cycles; }
 
 // How the SMs are shared out between the two persistent kernels of a world step (tensor-core member form).
-// The opponent kernel is bound by the SMs it gets (~14 us per 128-episode job, ~12 us to get going); a member job streams 512 KB and takes ~8.6 us on its SM until the HBM rate (~6 TB/s over all member CTAs)
-// becomes the limit.  Both end when their slowest CTA ends, so the split that minimises the later of the two is
+// The opponent kernel is bound by the SMs it gets (~14 us per 128-episode job, ~12 us to get going); a member job
+// streams 512 KB and takes ~8.6 us on its SM until the HBM rate (~6 TB/s over all member CTAs) becomes the limit.  Both end when their slowest CTA ends, so the split that minimises the later of the two is
 // found by trying every one (148 candidates, host side).
 static void ls_split_sms(int n_sm, int opp_jobs, int mem_jobs, int* g_opp, int* g_mem) {
     double best = 1e30;

@@ -1,1 +1,1 @@
-for g in "44 104" "48 100" "52 96" "56 92" "60 88" "64 84"; do set -- $g; echo -n "opp=$1 mem=$2: "; CEV_LS_GRID_OPP=$1 CEV_LS_GRID_MEM=$2 timeout 200 python scripts/time_roles.py 2>/dev/null | head -1 | cut -d: -f2 | cut -d, -f1; done
+timeout 600 python -m pytest tests/test_gpu_rollout.py -x -q -m gpu -k "extreme" 2>&1 | tail -15

@@ -52,13 +52,15 @@ def _compare(out, ref, label):
     return n_safe, n_fork
 
 
-def _structured_case(member_role, P, K, E, seed, n_cycles=25, init_shared=False, variant=0):
+def _structured_case(member_role, P, K, E, seed, n_cycles=25, init_shared=False, variant=0, tweak=None):
     from coevonet_b200 import layout, ops
     seats = layout.SEATS
     ms = layout.SEAT_OF[member_role]
     others = [s for s in range(3) if s != ms]
     counts = {seats[ms]: P, seats[others[0]]: K, seats[others[1]]: K}
     nets = _nets(counts["adversary_0"], counts["agent_0"], counts["agent_1"], seed)
+    if tweak is not None:
+        tweak(nets, ms)
     n = P * K * E
     init_all = mpe_env.draw_initial_states(K * E if init_shared else n, seed=seed)
     init = init_all.reshape((K, E, 11) if init_shared else (P, K, E, 11))
@@ -279,3 +281,23 @@ def test_roles_in_one_pass_equal_one_pass_per_role(P, K, E):
         single = ops.mpe_rollout(spec[0], spec[1], spec[2], spec[3], spec[4], variant=3, status=status)
         assert torch.equal(single, out), f"{spec[0]}: fused pass differs from the single-role pass"
     assert int(status.item()) == 0
+
+
+@pytest.mark.parametrize("w2_scale,g1_scale", [(250.0, 1.0), (0.01, 1.0), (1.0, 40.0), (30.0, 0.02)])
+def test_lockstep_opponents_with_extreme_weight_scales(w2_scale, g1_scale):
+    """The opponent kernel scales its FP16 operands by powers of two taken from max |fc2.W| and from the LayerNorm-1
+    parameters: opponents whose fc2 matrix or ln1.gamma are orders of magnitude away from an initialised network
+    must still agree with the fp32 oracle (same margin criterion as every other rollout test)."""
+    def tweak(nets, ms):
+        for seat, role in enumerate(("adversary_0", "agent_0", "agent_1")):
+            if seat == ms:
+                continue
+            in_dim = olayout.OBS_DIM[role]
+            rows = nets[role]
+            fc1 = 512 * in_dim
+            rows[:, fc1 + 512:fc1 + 1024] *= np.float32(g1_scale)                       # ln1.gamma
+            fc2w = fc1 + 3 * 512
+            rows[:, fc2w:fc2w + 256 * 512] *= np.float32(w2_scale)                       # fc2.W
+            # keep the pre-LayerNorm-2 scale sane for the comparison: LayerNorm-2 normalises it away anyway
+    out, ref = _structured_case("agent_0", 24, 1, 16, seed=4321, variant=3, tweak=tweak)
+    _compare(out, ref, f"lockstep opponents fc2.W x{w2_scale} ln1.gamma x{g1_scale}")

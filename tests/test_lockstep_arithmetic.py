@@ -60,3 +60,49 @@ def test_three_tf32_products_reach_fp32_accuracy():
     # one TF32 pass alone is three orders of magnitude worse: that is why the kernel issues three MMAs
     single = rd(h) @ rd(w).T
     assert np.max(np.abs(single - exact) / scale) > 2.0 ** -13
+
+
+def _scale_exp(bound, target):
+    """ls_scale_exp (rollout_lockstep.cu): 2^s * bound < 2^(target + 1), clamped to [-40, 40]."""
+    if not (bound > 0) or not np.isfinite(bound):
+        return 0
+    return int(np.clip(target - int(np.floor(np.log2(np.float32(bound)))), -40, 40))
+
+
+def _fp16_split(v):
+    """v' -> (fp16(v'), fp16(v' - fp16(v'))), as the opponent kernel's producers and ls_split_w2_kernel do."""
+    hi = v.astype(np.float16)
+    lo = (v - hi.astype(np.float32)).astype(np.float32).astype(np.float16)
+    return hi, lo
+
+
+def test_scaled_two_term_fp16_products_reach_fp32_accuracy():
+    """The opponent kernel since round 2: x1.w1 + x2.w1 + x1.w2 with power-of-two scaled FP16 hi / lo parts
+    (kind::f16 MMAs, fp32 accumulation, the accumulator unscaled by an exact power of two).  Checked over weight
+    and LayerNorm-parameter magnitudes far outside what training produces: the scales must keep every hi part
+    finite and the product at fp32 rounding level."""
+    rng = np.random.default_rng(11)
+    K, rows, cols = 512, 64, 48
+    for w_mag, gamma, beta in ((1 / np.sqrt(K), 1.0, 0.0), (300.0, 1.0, 0.0), (1e-6, 1.0, 0.0), (0.05, 80.0, 5.0),
+                               (0.05, 1e-3, 0.0), (2e4, 40.0, 100.0)):
+        # post-ReLU LayerNorm outputs: |x| <= sqrt(511) * gamma + beta
+        z = rng.normal(0.0, 1.0, (rows, K))
+        z[0, 0] = np.sqrt(511.0)                                  # the bound is attained
+        h = np.maximum(z * gamma + beta, 0).astype(np.float32)
+        w = rng.uniform(-w_mag, w_mag, (cols, K)).astype(np.float32)
+        sw = _scale_exp(np.abs(w).max(), 14)
+        sx = _scale_exp(22.63 * gamma + beta, 13)
+        hs, ws = np.ldexp(h, sx).astype(np.float32), np.ldexp(w, sw).astype(np.float32)
+        assert np.abs(ws).max() < 2.0 ** 15 and hs.max() < 2.0 ** 14 <= 65504          # inside fp16's range
+        x1, x2 = _fp16_split(hs)
+        w1, w2 = _fp16_split(ws)
+        assert np.all(np.isfinite(x1.astype(np.float32))) and np.all(np.isfinite(w1.astype(np.float32)))
+        f = lambda t: t.astype(np.float64)
+        acc = f(x2) @ f(w1).T + f(x1) @ f(w2).T + f(x1) @ f(w1).T
+        got = acc * 2.0 ** -(sw + sx)
+        exact = f(h) @ f(w).T
+        scale = np.abs(f(h)) @ np.abs(f(w)).T
+        assert np.max(np.abs(got - exact) / scale) < 2.0 ** -20, (w_mag, gamma, beta)
+    # a single FP16 pass is three orders of magnitude worse
+    one = (f(x1) @ f(w1).T) * 2.0 ** -(sw + sx)
+    assert np.max(np.abs(one - exact) / scale) > 2.0 ** -14
