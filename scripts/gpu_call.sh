@@ -1,1 +1,2 @@
-timeout 600 python -m pytest tests/test_gpu_rollout.py -x -q -m gpu -k "extreme" 2>&1 | tail -15
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
