@@ -81,9 +81,8 @@ int cev_destroy(cev_handle* h) {
     }
     if (h->env_stream) {
         cudaStreamDestroy(h->env_stream);
-        cudaStreamDestroy(h->opp_stream2[0]);
-        cudaStreamDestroy(h->opp_stream2[1]);
-        cudaStreamDestroy(h->mem_stream2);
+        for (int i = 0; i < 3; ++i) cudaStreamDestroy(h->opp_stream2[i]);
+        for (int i = 0; i < 2; ++i) cudaStreamDestroy(h->mem_stream2[i]);
         for (int r = 0; r < CEV_MAX_ROLES; ++r) {
             cudaEventDestroy(h->ev_opp[r]);
             cudaEventDestroy(h->ev_mem[r]);

@@ -303,7 +303,7 @@ struct cev_handle {
     cudaStream_t side_stream;           // the opponent kernel of the lockstep rollout runs beside the member kernel
     cudaEvent_t fork_ev, join_ev;
     // several roles in one lockstep pass (launch_rollout_lockstep_roles): environment steps on a third stream
-    cudaStream_t env_stream, opp_stream2[2], mem_stream2;
+    cudaStream_t env_stream, opp_stream2[3], mem_stream2[2];
     cudaEvent_t ev_opp[CEV_MAX_ROLES], ev_mem[CEV_MAX_ROLES], ev_env[CEV_MAX_ROLES];
     // optional per-kernel timing of the lockstep rollout (cev_kernel_timing_*): CUDA events recorded
     // around every member / opponent kernel launch on the launch stream

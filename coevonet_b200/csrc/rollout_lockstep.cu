@@ -1106,9 +1106,8 @@ int launch_rollout_lockstep_roles(cev_handle* h, const ClusterParams* ps, int n_
         static const int prio = getenv("CEV_LS_PRIO") ? atoi(getenv("CEV_LS_PRIO")) : 0;   // development aid
         const int p_opp = prio == 1 ? lo : mid, p_mem = prio == 2 ? (hi < lo - 1 ? lo - 2 : lo) : lo;
         CEV_CUDA(cudaStreamCreateWithPriority(&h->env_stream, cudaStreamNonBlocking, hi));
-        CEV_CUDA(cudaStreamCreateWithPriority(&h->opp_stream2[0], cudaStreamNonBlocking, p_opp));
-        CEV_CUDA(cudaStreamCreateWithPriority(&h->opp_stream2[1], cudaStreamNonBlocking, p_opp));
-        CEV_CUDA(cudaStreamCreateWithPriority(&h->mem_stream2, cudaStreamNonBlocking, p_mem));
+        for (int i = 0; i < 3; ++i) CEV_CUDA(cudaStreamCreateWithPriority(&h->opp_stream2[i], cudaStreamNonBlocking, p_opp));
+        for (int i = 0; i < 2; ++i) CEV_CUDA(cudaStreamCreateWithPriority(&h->mem_stream2[i], cudaStreamNonBlocking, p_mem));
         for (int r = 0; r < CEV_MAX_ROLES; ++r) {
             CEV_CUDA(cudaEventCreateWithFlags(&h->ev_opp[r], cudaEventDisableTiming));
             CEV_CUDA(cudaEventCreateWithFlags(&h->ev_mem[r], cudaEventDisableTiming));
@@ -1119,13 +1118,17 @@ int launch_rollout_lockstep_roles(cev_handle* h, const ClusterParams* ps, int n_
     // role's CTAs retire (no idle tail at the end of every kernel, launch latency hidden).
     static const int alt = getenv("CEV_LS_ALT") ? atoi(getenv("CEV_LS_ALT")) : 1;
     static const int skip = getenv("CEV_LS_SKIP") ? atoi(getenv("CEV_LS_SKIP")) : 0;   // development aid, see the single-role path
-    cudaStream_t s_mem[2] = {stream, alt ? h->mem_stream2 : stream};
-    cudaStream_t s_opp[2] = {h->opp_stream2[0], alt ? h->opp_stream2[1] : h->opp_stream2[0]};
+    // ns streams per kind: 2 by default (alt = 0: one; CEV_LS_NSTREAMS=3: development aid)
+    static const int ns_env = getenv("CEV_LS_NSTREAMS") ? atoi(getenv("CEV_LS_NSTREAMS")) : 2;
+    const int ns = alt ? (ns_env >= 3 ? 3 : 2) : 1;
+    cudaStream_t s_mem[3] = {stream, h->mem_stream2[0], h->mem_stream2[1]};
+    cudaStream_t s_opp[3] = {h->opp_stream2[0], h->opp_stream2[1], h->opp_stream2[2]};
     cudaStream_t s_env = h->env_stream;
     CEV_CUDA(cudaEventRecord(h->fork_ev, stream));                  // everything before this call is on `stream`
-    CEV_CUDA(cudaStreamWaitEvent(s_opp[0], h->fork_ev, 0));
-    CEV_CUDA(cudaStreamWaitEvent(s_opp[1], h->fork_ev, 0));
-    CEV_CUDA(cudaStreamWaitEvent(s_mem[1], h->fork_ev, 0));
+    for (int k = 0; k < ns; ++k) {
+        CEV_CUDA(cudaStreamWaitEvent(s_opp[k], h->fork_ev, 0));
+        if (k > 0) CEV_CUDA(cudaStreamWaitEvent(s_mem[k], h->fork_ev, 0));
+    }
     CEV_CUDA(cudaStreamWaitEvent(s_env, h->fork_ev, 0));
     // Every role's preparation goes on the streams of its first kernels: the opponents' split / statistics in front
     // of its first opponent kernel, the members' statistics and the initial states in front of its first member
@@ -1133,11 +1136,11 @@ int launch_rollout_lockstep_roles(cev_handle* h, const ClusterParams* ps, int n_
     // side and behind one another's first kernels instead of one after the other in front of the whole pass.
     LsRoleCtx ctx[CEV_MAX_ROLES];
     for (int r = 0; r < n_roles; ++r) {
-        rc = ls_build_role(h, ps[r], static_cast<char*>(h->ls_workspace) + per_role * r, s_opp[r & 1], s_mem[r & 1], &ctx[r]);
+        rc = ls_build_role(h, ps[r], static_cast<char*>(h->ls_workspace) + per_role * r, s_opp[r % ns], s_mem[r % ns], &ctx[r]);
         if (rc) return rc;
         ctx[r].ep.last = ps[r].n_cycles == 0;
-        ls_init_kernel<<<ctx[r].env_blocks, 256, 0, s_mem[r & 1]>>>(ctx[r].ep);
-        CEV_CUDA(cudaEventRecord(h->ev_env[r], s_mem[r & 1]));
+        ls_init_kernel<<<ctx[r].env_blocks, 256, 0, s_mem[r % ns]>>>(ctx[r].ep);
+        CEV_CUDA(cudaEventRecord(h->ev_env[r], s_mem[r % ns]));
     }
     int opp_grid = 0, mem_grid = 0;
     ls_split_sms(h->n_sm, ctx[0].op.n_jobs, ctx[0].tp.n_jobs, &opp_grid, &mem_grid);
@@ -1152,7 +1155,7 @@ int launch_rollout_lockstep_roles(cev_handle* h, const ClusterParams* ps, int n_
     int i = 0;
     for (int c = 0; c < n_cycles; ++c) {
         for (int r = 0; r < n_roles; ++r, ++i) {
-            cudaStream_t so = s_opp[i & 1], sm = s_mem[i & 1];
+            cudaStream_t so = s_opp[i % ns], sm = s_mem[i % ns];
             // this role's previous environment step (c = 0: its initial states, issued on the member stream)
             CEV_CUDA(cudaStreamWaitEvent(so, h->ev_env[r], 0));
             if (c > 0) CEV_CUDA(cudaStreamWaitEvent(sm, h->ev_env[r], 0));
@@ -1171,11 +1174,13 @@ int launch_rollout_lockstep_roles(cev_handle* h, const ClusterParams* ps, int n_
     // other streams are joined too (with no world step to play they hold the preparation and the initial states)
     CEV_CUDA(cudaEventRecord(h->join_ev, s_env));
     CEV_CUDA(cudaStreamWaitEvent(stream, h->join_ev, 0));
-    cudaStream_t others[3] = {s_opp[0], s_opp[1], s_mem[1]};
-    for (int k = 0; k < 3; ++k) {
-        if (others[k] == stream) continue;
-        CEV_CUDA(cudaEventRecord(h->ev_opp[k], others[k]));
+    for (int k = 0; k < ns; ++k) {
+        CEV_CUDA(cudaEventRecord(h->ev_opp[k], s_opp[k]));
         CEV_CUDA(cudaStreamWaitEvent(stream, h->ev_opp[k], 0));
+        if (k > 0) {
+            CEV_CUDA(cudaEventRecord(h->ev_mem[k], s_mem[k]));
+            CEV_CUDA(cudaStreamWaitEvent(stream, h->ev_mem[k], 0));
+        }
     }
     return check_cuda(cudaGetLastError(), "rollout_lockstep (roles) launch");
 }
