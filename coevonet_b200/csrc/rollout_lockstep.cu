@@ -64,6 +64,7 @@ struct LsBuffers {
     uint32_t* wmax;    // [2 seats][K] bit pattern of max |fc2.W|
     float* oscale;     // [2 seats][K][2]: 2^s_x (activation scale), 2^-(s_w + s_x) (accumulator unscale)
     double* l1stats;   // [2 seats][K][132]
+    float2* l1ms;      // [2 opponent seats][N]: LayerNorm-1 (mean, rstd) of every episode's current observation
     double* ml1stats;  // [P][132]  the members' own layer-1 statistics (tensor-core member form)
 };
 
@@ -89,6 +90,7 @@ static size_t ls_carve(void* base, int64_t N, int K, int P, LsBuffers* b) {
     t.act = static_cast<int32_t*>(take((size_t)3 * N * sizeof(int32_t)));
     t.gap = static_cast<float*>(take((size_t)3 * N * sizeof(float)));
     t.l1stats = static_cast<double*>(take((size_t)2 * K * LS_L1S * sizeof(double)));
+    t.l1ms = static_cast<float2*>(take((size_t)2 * N * sizeof(float2)));
     t.ml1stats = static_cast<double*>(take((size_t)P * LS_L1S * sizeof(double)));
     if (b) *b = t;
     return off;
@@ -126,7 +128,32 @@ __device__ __forceinline__ void ls_load_state(const LsBuffers& b, int64_t N, int
     }
     s.goal = b.goal[ep];
 }
-__device__ __forceinline__ void ls_store_obs(const LsBuffers& b, int64_t N, int64_t ep, const EnvState& s) {
+// LayerNorm-1 statistics of y = W1 x + b1 in closed form (fp64): mean = wbar . z, var = z^T C z with z = [x; 1] and
+// S = wbar[11] | C[11][11] of the network (ls_l1stats_kernel).  Returns (mean, 1 / sqrt(var + eps)).
+__device__ __forceinline__ float2 ls_row_stats(const double* __restrict__ S, const float* __restrict__ x, int in, bool& finite) {
+    double z[11];
+#pragma unroll
+    for (int a = 0; a < 11; ++a) z[a] = a < in ? (double)x[a] : (a == in ? 1.0 : 0.0);
+    double md = 0.0, vd = 0.0;
+#pragma unroll
+    for (int a = 0; a < 11; ++a) {
+        md = fma(__ldg(S + a), z[a], md);
+        double ra = 0.0;
+#pragma unroll
+        for (int b = 0; b < 11; ++b) ra = fma(__ldg(S + 11 + a * 11 + b), z[b], ra);
+        vd = fma(ra, z[a], vd);
+    }
+    const float m1 = (float)md, var = (float)vd;
+    finite = isfinite(m1) && isfinite(var);
+    return make_float2(m1, 1.0f / sqrtf(var + LN_EPS));
+}
+
+// Observations of the three seats, and for the two OPPONENT seats the LayerNorm-1 statistics of the opponent
+// network on that observation (one thread per episode here instead of a serial phase in front of every job of the
+// opponent kernel, where four of its eight producer warps computed them while the other four waited).
+__device__ __forceinline__ bool ls_store_obs(const LsBuffers& b, int64_t N, int64_t ep, const EnvState& s, int K, int E,
+                                             const int (&opp_seat)[2]) {
+    bool ok = true;
 #pragma unroll
     for (int seat = 0; seat < 3; ++seat) {
         float o[LS_OBS_PAD];
@@ -137,7 +164,16 @@ __device__ __forceinline__ void ls_store_obs(const LsBuffers& b, int64_t N, int6
         dst[0] = make_float4(o[0], o[1], o[2], o[3]);
         dst[1] = make_float4(o[4], o[5], o[6], o[7]);
         dst[2] = make_float4(o[8], o[9], o[10], o[11]);
+#pragma unroll
+        for (int oi = 0; oi < 2; ++oi)
+            if (seat == opp_seat[oi]) {
+                const int k = (int)((ep / E) % K);
+                bool fin;
+                b.l1ms[(int64_t)oi * N + ep] = ls_row_stats(b.l1stats + (size_t)(oi * K + k) * LS_L1S, o, seat_in_dim(seat), fin);
+                ok = ok && fin;
+            }
     }
+    return ok;
 }
 
 struct LsEnvParams {
@@ -150,6 +186,8 @@ struct LsEnvParams {
     // instead of the networks' (teacher forcing), and record the networks' own decisions
     const int32_t* forced;   // this cycle's [3][N]
     int32_t* act_out;        // this cycle's [3][N]
+    int opp_seat[2];         // the two opponent seats (ascending)
+    int32_t* status;
 };
 
 __global__ void __launch_bounds__(256) ls_init_kernel(const LsEnvParams p) {
@@ -165,7 +203,7 @@ __global__ void __launch_bounds__(256) ls_init_kernel(const LsEnvParams p) {
     p.b.acc[p.N + ep] = 0.0;
     p.b.acc[2 * p.N + ep] = 0.0;
     p.b.min_gap[ep] = CUDART_INF_F;
-    ls_store_obs(p.b, p.N, ep, s);
+    if (!ls_store_obs(p.b, p.N, ep, s, p.K, p.E, p.opp_seat) && p.status) atomicOr(p.status, CEV_STATUS_NONFINITE);
     if (p.last) {   // n_cycles == 0: nothing is played
         double* o = p.out + ep * CEV_ROLLOUT_OUT_DIM;
         o[0] = 0.0;
@@ -210,7 +248,7 @@ __global__ void __launch_bounds__(256) ls_env_step_kernel(const LsEnvParams p) {
     p.b.acc[2 * p.N + ep] = sum_adv;
     p.b.min_gap[ep] = min_gap;
     ls_store_state(p.b, p.N, ep, s);
-    ls_store_obs(p.b, p.N, ep, s);
+    if (!ls_store_obs(p.b, p.N, ep, s, p.K, p.E, p.opp_seat) && p.status) atomicOr(p.status, CEV_STATUS_NONFINITE);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -406,7 +444,7 @@ struct LsOppParams {
     const float* obs;        // [3][N][12]
     int32_t* act;            // [3][N]
     float* gap;
-    const double* l1stats;
+    const float2* l1ms;      // [2 opponent seats][N] LayerNorm-1 (mean, rstd) per episode (ls_store_obs)
     const float* oscale;     // [2 seats][K][2]: activation scale, accumulator unscale
     int32_t* status;
     float* logits;           // this cycle's [3][N][5] (parity instrumentation; null in production)
@@ -668,61 +706,29 @@ ls_opp_kernel(const __grid_constant__ CUtensorMap map_b, const LsOppParams p) {
             const float sx = __ldg(p.oscale + okey * 2);               // 2^s_x of this opponent
             // observations of this thread's four episode rows lane + 32 j
             float x[4][IN_GOOD];
+            int64_t epj[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int64_t jrow = (int64_t)tile * Geo::ROWS_PER_JOB + lane + 32 * j;
                 const int64_t jj = jrow < p.PE ? jrow : p.PE - 1;
                 const int64_t ep = ((jj / p.E) * p.K + k) * p.E + (jj % p.E);
+                epj[j] = ep;
                 const float4* src = reinterpret_cast<const float4*>(p.obs + ((int64_t)seat * p.N + ep) * LS_OBS_PAD);
                 const float4 v0 = __ldg(src), v1 = __ldg(src + 1), v2 = __ldg(src + 2);
                 x[j][0] = v0.x; x[j][1] = v0.y; x[j][2] = v0.z; x[j][3] = v0.w;
                 x[j][4] = v1.x; x[j][5] = v1.y; x[j][6] = v1.z; x[j][7] = v1.w;
                 x[j][8] = v2.x; x[j][9] = v2.y;
             }
-            // the job's first stage: acquire it now, its A-hi tile doubles as the exchange buffer of the
-            // LayerNorm-1 statistics (computed once per row by warps 0..3, read by all eight)
-            {
-                const uint32_t st = it % Geo::STAGES, use = it / Geo::STAGES;
-                if (use > 0) tc_mbar_wait(bar_empty + st, (use - 1) & 1);
-            }
-            float2* xch = reinterpret_cast<float2*>(stage_mem + (size_t)(it % Geo::STAGES) * Geo::STAGE_BYTES);
-            if (c < 4) {
-                // closed form (fp64): mean = wbar . z, var = z^T C z, z = [x; 1], for row lane + 32 c
-                const double* S = p.l1stats + (size_t)okey * LS_L1S;
-                double z[11];
-#pragma unroll
-                for (int a = 0; a < 11; ++a) {
-                    float xv = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (j == c && a < IN_GOOD) xv = x[j][a];
-                    z[a] = a < in ? (double)xv : (a == in ? 1.0 : 0.0);
-                }
-                double md = 0.0, vd = 0.0;
-#pragma unroll
-                for (int a = 0; a < 11; ++a) {
-                    md = fma(__ldg(S + a), z[a], md);
-                    double ra = 0.0;
-#pragma unroll
-                    for (int b = 0; b < 11; ++b) ra = fma(__ldg(S + 11 + a * 11 + b), z[b], ra);
-                    vd = fma(ra, z[a], vd);
-                }
-                const float m1 = (float)md, var = (float)vd;
-                if (!isfinite(m1) || !isfinite(var)) *flag = 1;
-                xch[lane + 32 * c] = make_float2(m1, 1.0f / sqrtf(var + LN_EPS));
-            }
-            asm volatile("bar.sync 1, 256;\n" ::: "memory");
             float mean[4], rstd[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float2 v = xch[lane + 32 * j];
+                const float2 v = __ldg(p.l1ms + (int64_t)oi * p.N + epj[j]);
                 mean[j] = v.x;
                 rstd[j] = v.y;
             }
-            asm volatile("bar.sync 1, 256;\n" ::: "memory");          // exchange buffer read: the tile may be written
             for (int kt = 0; kt < OP_KT; ++kt, ++it) {
                 const uint32_t st = it % Geo::STAGES, use = it / Geo::STAGES;
-                if (kt > 0 && use > 0) tc_mbar_wait(bar_empty + st, (use - 1) & 1);
+                if (use > 0) tc_mbar_wait(bar_empty + st, (use - 1) & 1);
                 unsigned char* a_hi = stage_mem + (size_t)st * Geo::STAGE_BYTES;
                 unsigned char* a_lo = a_hi + OP_A_BYTES;
 #if !(defined(CEV_EXP) && (CEV_EXP & 1))      // development experiment: bit 0 = producers write nothing
@@ -934,6 +940,9 @@ static int ls_build_role(cev_handle* h, const ClusterParams& p, void* ws, cudaSt
     ep.pos_first = p.pos_first;
     ep.init = p.init;
     ep.out = p.out;
+    ep.opp_seat[0] = seat_of[0];
+    ep.opp_seat[1] = seat_of[1];
+    ep.status = p.status;
     c->env_blocks = (int)((N + 255) / 256);
 
     const int KE = p.K * p.E;
@@ -957,7 +966,7 @@ static int ls_build_role(cev_handle* h, const ClusterParams& p, void* ws, cudaSt
     op.obs = b.obs;
     op.act = b.act;
     op.gap = b.gap;
-    op.l1stats = b.l1stats;
+    op.l1ms = b.l1ms;
     op.oscale = b.oscale;
     op.status = p.status;
 
