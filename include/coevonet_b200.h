@@ -75,8 +75,8 @@ typedef struct {
                                     (utils/game_logic_functions.py:127,195) */
     int32_t integrate_pos_first; /* SURVEY.md Appendix A.4 switch (1 = PettingZoo >= 1.24) */
     int32_t variant;             /* 0 auto (from THIS call's P*K*E), 1 generic kernel, 2 cluster kernel (member
-                                    weights resident in shared memory), 3 lockstep kernels (opponent forwards on
-                                    tcgen05).  A sharded caller passes the variant chosen for the GLOBAL
+                                    weights resident in shared memory), 3 lockstep kernels (member and opponent
+                                    forwards on tcgen05).  A sharded caller passes the variant chosen for the GLOBAL
                                     population (cev_mpe_rollout_plan) so every rank runs the same arithmetic. */
     int32_t reserved;
 } cev_rollout_cfg;
@@ -134,8 +134,8 @@ int cev_mpe_rollout_roles_f32(cev_handle* h, int n_roles, const cev_rollout_role
  *   forced_actions  int32: actions the world step replays instead of the networks' own
  *                   (the oracle's trace: FCNetwork.forward is then compared logit by logit on
  *                   identical observations, MPE/fcnetwork.py:37-70)
- *   logits_out      fp32 [..][5]: the logits behind every decision (member forward on the FP32
- *                   pipe, opponent forwards on tcgen05)
+ *   logits_out      fp32 [..][5]: the logits behind every decision (member and opponent forwards
+ *                   on tcgen05: 3xTF32 / scaled two-term FP16 with fp32 accumulation)
  *   actions_out     int32: the networks' own first-max decisions (MPE/fcnetwork.py:73-90)
  */
 int cev_mpe_rollout_trace_f32(cev_handle* h, int member_seat,
