@@ -470,7 +470,9 @@ __device__ __forceinline__ void op_produce_chunk(const float* __restrict__ w1a, 
         const float4 bb = *reinterpret_cast<const float4*>(fc1b + k0 + 4 * half);
         const float4 gg = *reinterpret_cast<const float4*>(ln1g + k0 + 4 * half);
         const float4 ee = *reinterpret_cast<const float4*>(ln1b + k0 + 4 * half);
-        const float bq[4] = {bb.x, bb.y, bb.z, bb.w}, gq[4] = {gg.x, gg.y, gg.z, gg.w}, eq[4] = {ee.x, ee.y, ee.z, ee.w};
+        // gamma and beta carry the activation scale 2^s_x: relu(fma(t, g, e)) * 2^s = relu(fma(t, g 2^s, e 2^s)) exactly
+        const float bq[4] = {bb.x, bb.y, bb.z, bb.w}, gq[4] = {gg.x * sx, gg.y * sx, gg.z * sx, gg.w * sx},
+                    eq[4] = {ee.x * sx, ee.y * sx, ee.z * sx, ee.w * sx};
         float hv[4][4];               // [row j][k]
 #pragma unroll
         for (int qq = 0; qq < 4; ++qq) {
@@ -488,7 +490,7 @@ __device__ __forceinline__ void op_produce_chunk(const float* __restrict__ w1a, 
 #pragma unroll
                 for (int i = 0; i < IN; ++i) pre = fmaf(w[i], x[j][i], pre);
                 pre += bq[qq];
-                hv[j][qq] = fmaxf(fmaf((pre - mean[j]) * rstd[j], gq[qq], eq[qq]), 0.f) * sx;
+                hv[j][qq] = fmaxf(fmaf((pre - mean[j]) * rstd[j], gq[qq], eq[qq]), 0.f);
             }
         }
 #pragma unroll

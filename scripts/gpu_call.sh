@@ -1,6 +1,3 @@
-mkdir -p gpurun_out
-timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r2g_bench_n1.json 2> gpurun_out/r2g_bench_n1.err; echo "bench rc=$?"; tail -2 gpurun_out/r2g_bench_n1.err
-python -c "
-import json; d=json.loads(open('gpurun_out/r2g_bench_n1.json').read().strip().splitlines()[-1])
-print(d['value']/1e6, d['ms_per_step'], d['e2e']['value']/1e6, d['parity']['member_match_frac'], d['roofline']['frac'], d['roofline']['whole_step']['frac_of_hbm_peak'], d['gpu_launches'], d['roofline']['second_kernel']['us_per_launch'], d['roofline']['us_per_launch'])"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/r2g_launches_bench.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-secondary > gpurun_out/r2g_ncu_bench.log 2>&1; echo "ncu launches rc=$?"
+timeout 900 python -m pytest tests/test_gpu_rollout.py tests/test_gpu_parity_r2.py -x -q -m gpu 2>&1 | tail -2
+CEV_LS_SKIP=2 CEV_LS_GRID_OPP=52 timeout 120 python scripts/time_ls.py
+for i in 1 2; do timeout 200 python scripts/time_roles.py 2>/dev/null | head -1 | cut -d: -f2 | cut -d, -f1; done
