@@ -19,12 +19,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ROLES = ("agent_0", "agent_1", "adversary_0")
 
 
-def _args(algorithm, P):
+def _args(algorithm, P, fitness_sharing=True):
     return types.SimpleNamespace(
         algorithm=algorithm, generations=2, population=P, hof_size=2, game="simple_adversary_v3",
         mutation_power_agent_0=0.05, mutation_power_agent_1=0.05, mutation_power_adversary=0.05,
         learning_rate=0.1, max_timesteps_per_episode=400, max_evaluation_steps=400, elites_number=2,
-        adaptive=False, max_mutation_power=0.5, min_mutation_power=0.001, fitness_sharing=True,
+        adaptive=False, max_mutation_power=0.5, min_mutation_power=0.001, fitness_sharing=fitness_sharing,
         early_stopping=False, patience=300, min_delta=0.1, debug=False, precision="float32", save=False,
         envs_per_member=1, reference_compat=True, init_states="device", seed=99, plots=False,
         record_history=True)
@@ -46,7 +46,7 @@ def _founders(P):
     return pop, hof, founder, theta
 
 
-def _run(rank, world, algorithm, P, port, q):
+def _run(rank, world, algorithm, P, port, q, fitness_sharing=True):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     torch.set_num_threads(1)
@@ -56,7 +56,7 @@ def _run(rank, world, algorithm, P, port, q):
     import oracle_backend
     from coevonet_b200 import engine
     comm = engine.Comm()
-    args = _args(algorithm, P)
+    args = _args(algorithm, P, fitness_sharing)
     pop, hof, founder, theta = _founders(P)
     shard = engine.Shard(P, comm.rank, comm.world)
     sl = slice(shard.row0, shard.row0 + shard.n_local)
@@ -75,16 +75,17 @@ def _run(rank, world, algorithm, P, port, q):
     else:
         out["rewards"] = np.stack([eng.history[g]["rewards"][r] for g in range(2) for r in ROLES])
         out["theta"] = np.stack([eng.theta[r].numpy()[:5000] for r in ROLES])
+        out["fitness"] = np.stack([eng.fitness[r].numpy() for r in ROLES])
     q.put(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def _launch(world, algorithm, P, port):
+def _launch(world, algorithm, P, port, fitness_sharing=True):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_run, args=(r, world, algorithm, P, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_run, args=(r, world, algorithm, P, port, q, fitness_sharing)) for r in range(world)]
     for p in procs:
         p.start()
     outs = [q.get(timeout=600) for _ in range(world)]
@@ -135,6 +136,22 @@ def test_es_two_ranks_match_one_rank():
         # |fitness| ~ 40 and lr/(n sigma) = 0.33 over 6 members): 1e-5 absolute on a delta of magnitude ~5
         np.testing.assert_allclose(o["theta"], single["theta"], rtol=0, atol=3e-5)
     assert np.array_equal(two[0]["theta"], two[1]["theta"])                              # replicas agree
+
+
+@pytest.mark.timeout(900)
+def test_es_two_ranks_without_fitness_sharing_gather_under_the_update():
+    """Without fitness sharing the update needs the local fitness only: the all-gather is started before and finished
+    after the three K6 calls (Comm.all_gather_rows_start).  Uneven shards (3 + 2); the gathered fitness is the
+    record every rank keeps."""
+    P = 5
+    single = _launch(1, "ES", P, 29621, fitness_sharing=False)[0]
+    two = _launch(2, "ES", P, 29622, fitness_sharing=False)
+    for o in two:
+        np.testing.assert_allclose(o["rewards"], single["rewards"], rtol=1e-12, atol=0)
+        np.testing.assert_allclose(o["fitness"], single["fitness"], rtol=1e-12, atol=0)
+        np.testing.assert_allclose(o["theta"], single["theta"], rtol=0, atol=3e-5)
+    assert np.array_equal(two[0]["theta"], two[1]["theta"])
+    assert np.array_equal(two[0]["fitness"], two[1]["fitness"])
 
 
 def _run_unseeded(rank, world, port, q):
