@@ -1141,17 +1141,19 @@ int launch_rollout_lockstep_roles(cev_handle* h, const ClusterParams* ps, int n_
         if (k > 0) CEV_CUDA(cudaStreamWaitEvent(s_mem[k], h->fork_ev, 0));
     }
     CEV_CUDA(cudaStreamWaitEvent(s_env, h->fork_ev, 0));
-    // Every role's preparation goes on the streams of its first kernels: the opponents' split / statistics in front
-    // of its first opponent kernel, the members' statistics and the initial states in front of its first member
-    // kernel (ev_env[r] tells the opponent stream that the initial observations exist), so the roles prepare side by
-    // side and behind one another's first kernels instead of one after the other in front of the whole pass.
+    // Every role's preparation goes on the streams of its first kernels: the opponents' split / statistics and the
+    // initial states in front of its first opponent kernel, the members' statistics in front of its first member
+    // kernel (ev_env[r] tells both streams that the initial observations exist), so the roles prepare side by side
+    // and behind one another's first kernels instead of one after the other in front of the whole pass.
     LsRoleCtx ctx[CEV_MAX_ROLES];
     for (int r = 0; r < n_roles; ++r) {
         rc = ls_build_role(h, ps[r], static_cast<char*>(h->ls_workspace) + per_role * r, s_opp[r % ns], s_mem[r % ns], &ctx[r]);
         if (rc) return rc;
         ctx[r].ep.last = ps[r].n_cycles == 0;
-        ls_init_kernel<<<ctx[r].env_blocks, 256, 0, s_mem[r % ns]>>>(ctx[r].ep);
-        CEV_CUDA(cudaEventRecord(h->ev_env[r], s_mem[r % ns]));
+        // the initial states go behind the opponents' preparation: ls_init_kernel evaluates the opponents'
+        // LayerNorm-1 statistics on the first observations and reads what ls_l1stats_kernel wrote
+        ls_init_kernel<<<ctx[r].env_blocks, 256, 0, s_opp[r % ns]>>>(ctx[r].ep);
+        CEV_CUDA(cudaEventRecord(h->ev_env[r], s_opp[r % ns]));
     }
     int opp_grid = 0, mem_grid = 0;
     ls_split_sms(h->n_sm, ctx[0].op.n_jobs, ctx[0].tp.n_jobs, &opp_grid, &mem_grid);
@@ -1167,9 +1169,9 @@ int launch_rollout_lockstep_roles(cev_handle* h, const ClusterParams* ps, int n_
     for (int c = 0; c < n_cycles; ++c) {
         for (int r = 0; r < n_roles; ++r, ++i) {
             cudaStream_t so = s_opp[i % ns], sm = s_mem[i % ns];
-            // this role's previous environment step (c = 0: its initial states, issued on the member stream)
+            // this role's previous environment step (c = 0: its initial states)
             CEV_CUDA(cudaStreamWaitEvent(so, h->ev_env[r], 0));
-            if (c > 0) CEV_CUDA(cudaStreamWaitEvent(sm, h->ev_env[r], 0));
+            CEV_CUDA(cudaStreamWaitEvent(sm, h->ev_env[r], 0));
             if (!(skip & 1)) ls_opp_kernel<<<opp_grid, OP_THREADS, OP_SMEM, so>>>(ctx[r].map_b, ctx[r].op);
             CEV_CUDA(cudaEventRecord(h->ev_opp[r], so));
             if (!(skip & 2)) ls_launch_member_tc(ctx[r], mem_grid, sm);
